@@ -1,0 +1,215 @@
+/*
+ * subsweep_b200.h -- C ABI of libsubsweep_b200.so: a B200-native (sm_100a) replacement for
+ * subsweep's per-timestep hot path, the directional upwind sweep over the Voronoi grid plus
+ * the per-cell hydrogen ionization/temperature chemistry.
+ *
+ * This is the boundary a thin Rust FFI crate binds (INTEGRATION.md shows the crate): plain
+ * pointers and sizes, no C++ or torch types.  Every entry point cites the reference interface
+ * it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - all floating point is f64 in SI base units, exactly like the reference's diman quantities
+ *     (src/units/mod.rs); indices are 0-based; cell order = ParticleId.index order
+ *     (src/sweep/active_list.rs:25-35).
+ *   - host arrays passed in are borrowed for the duration of the call only.
+ *   - every function returns 0 on success or a negative SSW_E_* code; ssw_last_error() gives
+ *     the message (thread-local).  The handle is not thread-safe: one caller thread, like the
+ *     reference's NonSend solver resource (src/sweep/mod.rs:139).
+ *   - there is no CPU fallback: without a CUDA device of compute capability 10.x every call
+ *     that needs the device fails with SSW_E_CUDA.
+ */
+#ifndef SUBSWEEP_B200_H
+#define SUBSWEEP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSW_ABI_VERSION 1
+
+enum {
+    SSW_OK = 0,
+    SSW_E_INVALID = -1,   /* bad argument / inconsistent grid                         */
+    SSW_E_CUDA = -2,      /* CUDA runtime error, no device, wrong architecture        */
+    SSW_E_DEADLOCK = -3,  /* dependency cycle among active Local faces: the reference */
+                          /* would spin forever in Sweep::solve (src/sweep/mod.rs:291-300) */
+    SSW_E_NOMEM = -4,
+    SSW_E_COMM = -5       /* the all-reduce hook failed                               */
+};
+
+/* ParticleType of a face's neighbour, single-process subset of src/sweep/grid/cell.rs:16-23.
+ * Remote / RemotePeriodic do not exist here: the MPI domain split is replaced by direction
+ * sharding, every process holds the whole grid. */
+enum { SSW_FACE_LOCAL = 0, SSW_FACE_BOUNDARY = 1, SSW_FACE_LOCAL_PERIODIC = 2 };
+
+/* SweepParameters (src/sweep/parameters.rs:8-46) + HydrogenOnly (src/chemistry/hydrogen_only/
+ * mod.rs:41-46) + what Sweep::new takes (src/sweep/mod.rs:194-232, call site :675-691). */
+typedef struct ssw_params {
+    int32_t n_dirs;                 /* D = sweep.directions (count)                              */
+    const double *dirs_xyz;         /* D x 3; table values as in direction/healpix.rs (NOT         */
+                                    /* re-normalised) or normalised explicit lists (mod.rs:97-109) */
+    int32_t n_levels;               /* sweep.num_timestep_levels                                   */
+    double max_timestep_s;          /* sweep.max_timestep                                          */
+    double timestep_safety_factor;  /* sweep.timestep_safety_factor (default 0.1)                  */
+    double chemistry_timestep_safety_factor; /* sweep.chemistry_timestep_safety_factor             */
+    double significant_rate_threshold_per_s; /* sweep.significant_rate_threshold (default 0)       */
+    int32_t prevent_cooling;        /* sweep.prevent_cooling (default true)                        */
+    double scale_factor;            /* Cosmology::scale_factor() (src/sweep/mod.rs:687)            */
+    int32_t check_deadlock;         /* sweep.check_deadlock                                        */
+    int32_t device_id;              /* CUDA device ordinal of this process                         */
+    int32_t rank, world_size;       /* direction sharding: this process sweeps the directions      */
+                                    /* ssw_direction_shard(D, world_size, rank); 0,1 = all         */
+    uint32_t flags;                 /* SSW_FLAG_*                                                  */
+} ssw_params;
+
+enum {
+    SSW_FLAG_NO_SCHEDULE_CACHE = 1u << 0, /* rebuild wavefront level sets every single sweep      */
+    SSW_FLAG_NO_COMPILED_PATH = 1u << 1   /* replay cached level sets from the generic task list   */
+};
+
+/* Flat (CSR) form of the per-particle `Cell` component (src/sweep/grid/cell.rs:92-133):
+ * cell c owns faces [face_offsets[c], face_offsets[c+1]) in the order of Cell::neighbours. */
+typedef struct ssw_grid {
+    uint64_t n_cells;
+    const uint64_t *face_offsets;  /* N+1                                                        */
+    const double *face_area;       /* F, Face::area                                               */
+    const double *face_normal;     /* F x 3, Face::normal (outward unit vector)                   */
+    const int32_t *face_neighbour; /* F, neighbour's ParticleId.index; -1 for Boundary            */
+    const uint8_t *face_kind;      /* F, SSW_FACE_*                                               */
+    const double *cell_size;       /* N, Cell::size                                               */
+    const double *cell_volume;     /* N, Cell::volume                                             */
+} ssw_grid;
+
+typedef struct ssw_handle ssw_handle;
+
+/* Fields readable per cell.  The first block are the per-particle components the reference
+ * writes back after every step (src/sweep/mod.rs:718-738, src/components.rs:14-83); the second
+ * block are the optional chemistry outputs (src/sweep/chemistry_output.rs:25-55). */
+typedef enum ssw_field {
+    SSW_F_XHII = 0,               /* ionized_hydrogen_fraction                                   */
+    SSW_F_TEMPERATURE = 1,        /* temperature [K]                                             */
+    SSW_F_TIMESTEP = 2,           /* timestep: chemistry's recommended timescale [s]             */
+    SSW_F_PHOTON_RATE = 3,        /* photon_rate = sum_d incoming_total_rate[d] [1/s]            */
+    SSW_F_CHANGE_TIMESCALE = 4,   /* Site::change_timescale [s]                                  */
+    SSW_F_PHOTOIONIZATION_RATE = 5,
+    SSW_F_HEATING_RATE = 6,
+    SSW_F_RECOMBINATION_RATE = 7,
+    SSW_F_COLLISIONAL_IONIZATION_RATE = 8,
+    SSW_F_PREVIOUS_RATE = 9,      /* Site::previous_incoming_total_rate                          */
+    SSW_F_DENSITY = 10,
+    SSW_F_SOURCE = 11,
+    SSW_F_IONIZATION_TIME = 12    /* ionization_time (src/sweep/mod.rs:731-738); NaN = not yet   */
+} ssw_field;
+
+/* all-reduce hook for direction sharding: sum `n` doubles in place over all ranks.  `buf` is a
+ * DEVICE pointer on params.device_id; `cuda_stream` is the cudaStream_t the library works on
+ * (work queued before the call is complete when the hook is entered; the hook must leave the
+ * result complete or ordered on that stream).  Replaces the MPI flux messages of
+ * src/sweep/communicator.rs:59-95. */
+typedef int (*ssw_allreduce_fn)(void *ctx, double *buf, uint64_t n, void *cuda_stream);
+
+/* -- life cycle ------------------------------------------------------------------------- */
+
+/* Sweep::new (src/sweep/mod.rs:194-232) + init_sweep_system (:634-692).  Copies the grid and
+ * the four per-cell components to the device; all cells start at level n_levels-1 (:206). */
+int ssw_create(const ssw_params *params, const ssw_grid *grid, const double *density,
+               const double *xhii, const double *temperature, const double *source,
+               ssw_handle **out);
+/* Drop (src/sweep/communicator.rs:116-125). */
+void ssw_destroy(ssw_handle *h);
+int ssw_set_allreduce(ssw_handle *h, ssw_allreduce_fn fn, void *ctx);
+
+/* -- the hot path ------------------------------------------------------------------------ */
+
+/* Sweep::run_sweeps (src/sweep/mod.rs:258-272): all single sweeps of one full step in the
+ * reference's level order, chemistry after each, then the timestep-level update.  Blocking.
+ * *time_elapsed_s receives the value the reference returns (added to SimulationTime, :716-717). */
+int ssw_run_sweeps(ssw_handle *h, double *time_elapsed_s);
+
+/* Refresh per-cell inputs between steps (the `Source` / `Density` components,
+ * src/sweep/mod.rs:637-644).  NULL leaves a field unchanged. */
+int ssw_set_inputs(ssw_handle *h, const double *density, const double *source);
+
+/* -- read-back (src/sweep/mod.rs:718-738, :612-632, :234-245) ---------------------------- */
+int ssw_read(ssw_handle *h, ssw_field field, double *out /* N */);
+int ssw_read_levels(ssw_handle *h, uint8_t *out /* N */);
+int ssw_level_counts(ssw_handle *h, uint64_t *out /* n_levels, cumulative: #cells with level >= l */);
+int ssw_lowest_allowed_level(ssw_handle *h, int32_t *out);
+
+/* -- pieces, exposed for parity tests and profiling --------------------------------------- */
+
+/* Sweep::single_sweep (src/sweep/mod.rs:274-289) at `level`, including chemistry. */
+int ssw_single_sweep(ssw_handle *h, int32_t level);
+/* force ActiveList levels (src/sweep/active_list.rs:135-153) */
+int ssw_set_levels(ssw_handle *h, const uint8_t *levels /* N */);
+int ssw_set_change_timescale(ssw_handle *h, const double *tau /* N */);
+/* Sweep::update_timestep_levels (src/sweep/mod.rs:576-589) with the current lowest allowed level */
+int ssw_update_timestep_levels(ssw_handle *h);
+/* per-direction state of this rank's directions, cell-major N x D_local like the reference's
+ * Site vectors (src/sweep/site.rs:12-23): which = 0 incoming_total_rate, 1 outgoing_total_rate,
+ * 2 periodic_source */
+int ssw_read_dir_state(ssw_handle *h, int32_t which, double *out /* N x D_local */);
+/* wavefront level of every cell for the active set of `level` and global direction `dir`
+ * (0 = initial task; -1 = inactive); the level sets the kernels iterate over. */
+int ssw_read_wavefront_levels(ssw_handle *h, int32_t level, int32_t dir, int32_t *out /* N */);
+
+typedef enum ssw_stat {
+    SSW_STAT_TASKS_SOLVED = 0,      /* cell-direction updates since create (this rank)          */
+    SSW_STAT_SINGLE_SWEEPS = 1,
+    SSW_STAT_CHEM_CELLS = 2,        /* chemistry cell updates                                   */
+    SSW_STAT_CHEM_FAILURES = 3,     /* TimestepConvergenceFailed (hydrogen_only/mod.rs:431-440)  */
+    SSW_STAT_SCHEDULE_BUILDS = 4,   /* wavefront level-set builds                               */
+    SSW_STAT_SCHEDULE_REPLAYS = 5,
+    SSW_STAT_KERNEL_LAUNCHES = 6,   /* kernels launched by this library since create            */
+    SSW_STAT_WAVEFRONT_LEVELS = 7,  /* level count of the last single sweep                     */
+    SSW_STAT_CHEM_ATTEMPTS = 8,     /* try_timestep_update calls                                 */
+    SSW_STAT_CHEM_MAX_DEPTH = 9
+} ssw_stat;
+int ssw_get_stat(ssw_handle *h, ssw_stat which, uint64_t *out);
+
+/* Device time (CUDA events, ms) accumulated per category since the last reset, named like the
+ * reference's Performance timers (src/sweep/mod.rs:275,550,577). */
+typedef struct ssw_timings {
+    double sweep_ms;          /* sum of sweep_level_<L>                                         */
+    double chemistry_ms;      /* "chemistry" (incl. rate reduction and all-reduce)              */
+    double update_levels_ms;  /* "update levels"                                                */
+    double schedule_ms;       /* level-set builds (part of sweep_level_<L> in the reference)    */
+    double allreduce_ms;
+    double sweep_kernel_ms;   /* the per-level sweep kernel(s) alone                            */
+    uint64_t sweep_kernel_launches;
+    uint64_t sweep_kernel_tasks;  /* cell-direction updates processed by those launches          */
+    double sweep_level_ms[32];
+} ssw_timings;
+int ssw_get_timings(ssw_handle *h, ssw_timings *out);
+int ssw_reset_timings(ssw_handle *h);
+
+/* -- helpers -------------------------------------------------------------------------------- */
+
+/* contiguous direction shard [begin, end) of rank `rank` out of `world_size` */
+int ssw_direction_shard(int32_t n_dirs, int32_t world_size, int32_t rank, int32_t *begin,
+                        int32_t *end);
+/* TimestepLevel::from_max_timestep_and_desired_timestep (src/sweep/timestep_level.rs:27-36),
+ * host-side scalar version of the device rule */
+int32_t ssw_level_from_timesteps(int32_t max_num_levels, double max_timestep, double desired);
+/* TimestepState::iter_levels_in_sweep_order (src/sweep/timestep_state.rs:22-27) */
+int32_t ssw_levels_in_sweep_order(int32_t max_num_levels, int32_t lowest_allowed, int32_t *out,
+                                  int32_t cap);
+/* one chemistry update of n independent cells on the device, for parity tests of
+ * HydrogenOnly::update_abundances (src/chemistry/hydrogen_only/mod.rs:90-119).  All arrays are
+ * HOST arrays of length n; xhii / temperature are updated in place. */
+int ssw_chemistry_batch(int32_t device_id, uint64_t n, double *xhii, double *temperature,
+                        const double *density, const double *volume, const double *length,
+                        const double *rate, const double *timestep, double scale_factor,
+                        double safety_factor, int32_t prevent_cooling, double *timescale_out,
+                        int32_t *process_out, int32_t *depth_out, uint64_t *attempts_out);
+
+const char *ssw_last_error(void);
+int32_t ssw_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUBSWEEP_B200_H */

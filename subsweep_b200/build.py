@@ -1,0 +1,58 @@
+"""Builds libsubsweep_b200.so in-tree with nvcc for sm_100a (no JIT cache, the .so travels with the repo)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+CSRC = ROOT / "csrc"
+LIB = ROOT / "lib" / "libsubsweep_b200.so"
+SOURCES = [CSRC / "sweep.cu"]
+HEADERS = [CSRC / "kernels.cuh", CSRC / "compiled.cuh", CSRC / "chemistry.cuh",
+           ROOT.parent / "include" / "subsweep_b200.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def is_stale() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    return any(p.stat().st_mtime > t for p in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile the CUDA library if it is missing or older than its sources."""
+    if not force and not is_stale():
+        return LIB
+    LIB.parent.mkdir(parents=True, exist_ok=True)
+    tmp = LIB.with_suffix(".so.tmp%d" % os.getpid())
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(tmp), *map(str, SOURCES)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        tmp.unlink(missing_ok=True)
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    os.replace(tmp, LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,545 @@
+// kernels.cuh -- sm_100a kernels of the sweep hot path (general path: any active set).
+//
+// Data layout in HBM:
+//   grid, static      face_geo[F]   double4 {nx, ny, nz, area}       one 32-B sector per face
+//                     face_rev[F]   double   area of the same face as stored by the neighbour
+//                     face_nb[F]    int32    neighbour cell, -1 boundary
+//                     face_kind[F]  uint8    SSW_FACE_*
+//                     face_off[N+1] uint32
+//   per cell          rho, x, T, ts, tau, prev_rate, src, size, volume, att (= exp(-n_HI sigma size)),
+//                     level (uint8), pidx (int32: row in the periodic tables or -1)
+//   per (dir, cell)   q[dl*N + c]        outgoing rate / total downwind effective area
+//                     incoming[dl*N + c] incoming_total_rate + source / D as read by the task
+//                     missing[dl*N + c]  int32, Kahn counters (build mode only)
+//   periodic rows     per_lag[dl*P + p], per_new[dl*P + p]
+//
+// The reference keeps incoming / outgoing / periodic_source accumulators per (cell, dir) and
+// scatters *corrections* (src/sweep/mod.rs:423-513).  Because every accumulator starts at zero
+// and every correction is (new_out - old_out) * share, the accumulators telescope to
+//     incoming[c][d]        = sum over Local    upwind faces  out[nb][d] * share(nb -> c, d)
+//     periodic_source[c][d] = sum over Periodic upwind faces  out[nb][d] * share(nb -> c, d)
+// at all times, with share = A * (n.d) / sum_downwind(A * (n.d)) evaluated on the donor's
+// faces.  The kernels therefore keep only q = out / sum_downwind(A n.d) per (cell, dir) and
+// GATHER: no atomics on flux, results independent of the order tasks run in.
+#pragma once
+#include <cooperative_groups.h>
+#include <cstdint>
+
+#include "chemistry.cuh"
+
+namespace ssw {
+namespace cg = cooperative_groups;
+
+constexpr int kMaxDirs = 128;
+__constant__ double c_dirs[kMaxDirs * 3];  // this rank's directions, local order
+
+struct GridView {
+    const double4 *face_geo;
+    const double *face_rev;
+    const int32_t *face_nb;
+    const uint8_t *face_kind;
+    const uint32_t *face_off;
+    uint32_t n_cells;
+};
+
+struct CellView {
+    double *rho, *x, *T, *ts, *tau, *prev_rate, *src, *att, *ion_time;
+    const double *size, *volume;
+    uint8_t *level;
+    const int32_t *pidx;
+};
+
+// glam DVec3::dot without FMA contraction: the sign decides upwind / downwind
+// (src/sweep/grid/cell.rs:126-132) and must match the CPU bit for bit.
+__device__ __forceinline__ double dot_dir(const double4 &g, const double dx, const double dy,
+                                          const double dz) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(g.x, dx), __dmul_rn(g.y, dy)), __dmul_rn(g.z, dz));
+}
+
+__device__ __forceinline__ double4 ld_geo(const double4 *p) {
+    // two 16-byte read-only loads (the grid is immutable after create)
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// ------------------------------------------------------------------------------------------
+// Kahn counters: Sweep::init_counts (src/sweep/mod.rs:346-386) + get_initial_tasks (:388-398)
+// one thread per (active cell, local direction); blockIdx.y = local direction.
+// ------------------------------------------------------------------------------------------
+struct QueueCtl {       // device-resident control block of one build
+    unsigned int cnt[3];  // pushes of level l go to cnt[(l+1)%3]; cnt[0] = initial tasks
+    unsigned int n_levels;
+    unsigned int solved;
+    unsigned int overflow;
+};
+
+__device__ __forceinline__ void warp_push(uint32_t *queue, unsigned int base, unsigned int *counter,
+                                          bool pred, uint32_t task) {
+    const unsigned mask = __activemask();
+    const unsigned ballot = __ballot_sync(mask, pred);
+    if (ballot == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(ballot) - 1;
+    unsigned int pos = 0;
+    if (lane == leader) pos = atomicAdd(counter, __popc(ballot));
+    pos = __shfl_sync(mask, pos, leader);
+    if (pred) queue[base + pos + __popc(ballot & ((1u << lane) - 1))] = task;
+}
+
+__global__ void __launch_bounds__(256)
+init_counts_kernel(GridView g, const uint8_t *__restrict__ level, int cur,
+                   const uint32_t *__restrict__ act_list, uint32_t n_act, int32_t *missing,
+                   uint32_t *queue, QueueCtl *ctl, int32_t *wlevel_dbg, int dl_base) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int dl = dl_base + blockIdx.y;
+    const bool valid = k < n_act;
+    uint32_t c = 0;
+    int m = 0;
+    if (valid) {
+        c = act_list ? act_list[k] : k;
+        const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+        const uint32_t f0 = g.face_off[c], f1 = g.face_off[c + 1];
+        for (uint32_t f = f0; f < f1; ++f) {
+            if (g.face_kind[f] != 0) continue;  // only Local faces carry dependencies
+            const double d = dot_dir(ld_geo(g.face_geo + f), dx, dy, dz);
+            if (!(d < 0.0)) continue;
+            if (level[g.face_nb[f]] >= cur) ++m;
+        }
+        missing[(size_t)dl * g.n_cells + c] = m;
+        if (wlevel_dbg && m == 0) wlevel_dbg[c] = 0;
+    }
+    warp_push(queue, 0, &ctl->cnt[0], valid && m == 0, (uint32_t)dl * g.n_cells + c);
+}
+
+// ------------------------------------------------------------------------------------------
+// one task: Sweep::solve_task (src/sweep/mod.rs:423-485) in gather form
+// ------------------------------------------------------------------------------------------
+struct SweepArgs {
+    GridView g;
+    const double *att;      // per cell
+    const double *src;      // per cell
+    const int32_t *pidx;    // per cell
+    const uint8_t *level;   // per cell
+    double *q;              // [dl][c]
+    double *incoming;       // [dl][c]
+    const double *per_lag;  // [dl][p]
+    int32_t *missing;       // [dl][c]
+    uint32_t n_periodic;
+    double inv_threshold_unused;
+    double threshold;
+    double n_dirs_total;    // D as f64 (source / D, src/sweep/site.rs:49-51)
+    int cur;
+};
+
+template <bool BUILD>
+__device__ __forceinline__ void solve_task(const SweepArgs &a, uint32_t task, uint32_t *queue,
+                                           unsigned int push_base, unsigned int *push_counter,
+                                           int32_t *wlevel_dbg, int wave, bool valid) {
+    const uint32_t N = a.g.n_cells;
+    uint32_t c = 0, dl = 0, f0 = 0, f1 = 0;
+    double dx = 0, dy = 0, dz = 0;
+    if (valid) {
+        dl = task / N;
+        c = task - dl * N;
+        dx = c_dirs[3 * dl];
+        dy = c_dirs[3 * dl + 1];
+        dz = c_dirs[3 * dl + 2];
+        f0 = a.g.face_off[c];
+        f1 = a.g.face_off[c + 1];
+    }
+    if (valid && a.q != nullptr) {
+        const double *qd = a.q + (size_t)dl * N;
+        double in = 0.0, ttot = 0.0;
+        for (uint32_t f = f0; f < f1; ++f) {
+            const double4 geo = ld_geo(a.g.face_geo + f);
+            const double d = dot_dir(geo, dx, dy, dz);
+            if (d < 0.0) {
+                if (a.g.face_kind[f] == 0) {
+                    const double w = __ldg(a.g.face_rev + f) * (-d);
+                    in += __ldcg(qd + a.g.face_nb[f]) * w;
+                }
+            } else if (d > 0.0) {
+                ttot += geo.w * d;
+            }
+        }
+        const double inc = in + a.src[c] / a.n_dirs_total;           // site.rs:49-56
+        const int32_t p = a.pidx[c];
+        const double total = p >= 0 ? inc + a.per_lag[(size_t)dl * a.n_periodic + p] : inc + 0.0;
+        // HydrogenOnly::get_outgoing_rate, hydrogen_only/mod.rs:81-87
+        const double out = (total < a.threshold) ? 0.0 : total * a.att[c];
+        __stcg(a.q + (size_t)dl * N + c, ttot > 0.0 ? out / ttot : 0.0);
+        __stcg(a.incoming + (size_t)dl * N + c, inc);
+    }
+    if (BUILD && valid && wlevel_dbg) wlevel_dbg[c] = wave;
+    if (BUILD) {
+        // handle_local_neighbour (src/sweep/mod.rs:487-503): release downwind active neighbours
+        __syncwarp();
+        uint32_t f = f0;
+        while (true) {
+            // find this thread's next downwind Local active face (warp-synchronous push needs
+            // all lanes to take part in every round)
+            bool have = false;
+            uint32_t nb = 0;
+            while (valid && f < f1) {
+                const uint32_t ff = f++;
+                if (a.g.face_kind[ff] != 0) continue;
+                const double d = dot_dir(ld_geo(a.g.face_geo + ff), dx, dy, dz);
+                if (!(d > 0.0)) continue;
+                nb = (uint32_t)a.g.face_nb[ff];
+                if (a.level[nb] < a.cur) continue;
+                have = true;
+                break;
+            }
+            if (__ballot_sync(0xffffffffu, have) == 0) break;
+            bool ready = false;
+            if (have) ready = atomicSub(a.missing + (size_t)dl * N + nb, 1) == 1;
+            warp_push(queue, push_base, push_counter, ready, dl * N + nb);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// BUILD: fused Kahn peeling + solve, persistent cooperative kernel.  Level l of the wavefront
+// is queue[start_l, end_l); tasks released while solving it are appended behind end_l, so when
+// the kernel ends `queue` is the level-sorted task list and ctl->n_levels / level_off describe
+// the level sets (north_star: "upwind dependencies are resolved on device into wavefront level
+// sets").  One grid barrier per level.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sweep_build_kernel(SweepArgs a, uint32_t *queue, QueueCtl *ctl, uint32_t *level_off,
+                   uint32_t level_off_cap, int32_t *wlevel_dbg) {
+    cg::grid_group grid = cg::this_grid();
+    const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int gsz = gridDim.x * blockDim.x;
+    unsigned int start = 0;
+    unsigned int end = ctl->cnt[0];
+    unsigned int lvl = 0;
+    while (start < end) {
+        if (gtid == 0) {
+            if (lvl < level_off_cap) level_off[lvl] = start;
+            else ctl->overflow = 1;
+            ctl->cnt[(lvl + 2) % 3] = 0;  // slot used by level lvl+1's pushes; nobody reads it now
+        }
+        unsigned int *counter = &ctl->cnt[(lvl + 1) % 3];
+        // every lane of every warp runs the same number of rounds (warp-synchronous pushes)
+        const unsigned int span = end - start;
+        const unsigned int rounds = (span + gsz - 1) / gsz;
+        for (unsigned int r = 0; r < rounds; ++r) {
+            const unsigned int i = start + r * gsz + gtid;
+            const bool valid = i < end;
+            const uint32_t task = valid ? __ldcg(queue + i) : 0u;
+            solve_task<true>(a, task, queue, end, counter, wlevel_dbg, (int)lvl, valid);
+        }
+        grid.sync();
+        start = end;
+        end = end + *((volatile unsigned int *)counter);
+        ++lvl;
+    }
+    if (gtid == 0) {
+        if (lvl < level_off_cap) level_off[lvl] = start;
+        else ctl->overflow = 1;
+        ctl->n_levels = lvl;
+        ctl->solved = start;
+    }
+}
+
+// REPLAY: the level sets are known (cached); same gather, no counters.  Persistent cooperative
+// kernel, one grid barrier per wavefront level.
+__global__ void __launch_bounds__(256)
+sweep_replay_kernel(SweepArgs a, const uint32_t *__restrict__ queue,
+                    const uint32_t *__restrict__ level_off, uint32_t n_levels) {
+    cg::grid_group grid = cg::this_grid();
+    const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int gsz = gridDim.x * blockDim.x;
+    for (uint32_t lvl = 0; lvl < n_levels; ++lvl) {
+        const uint32_t s = level_off[lvl], e = level_off[lvl + 1];
+        for (uint32_t i = s + gtid; i < e; i += gsz)
+            solve_task<false>(a, queue[i], nullptr, 0, nullptr, nullptr, 0, true);
+        if (lvl + 1 < n_levels) grid.sync();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// periodic_source rows: sum over LocalPeriodic upwind faces (handle_local_periodic_neighbour,
+// src/sweep/mod.rs:505-513, in gather form).  One thread per (periodic cell, local direction).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+periodic_gather_kernel(GridView g, const uint32_t *__restrict__ pcells, uint32_t n_periodic,
+                       const double *__restrict__ q, double *__restrict__ dst) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int dl = blockIdx.y;
+    if (p >= n_periodic) return;
+    const uint32_t c = pcells[p];
+    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    const double *qd = q + (size_t)dl * g.n_cells;
+    double acc = 0.0;
+    for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
+        if (g.face_kind[f] != 2) continue;
+        const double d = dot_dir(ld_geo(g.face_geo + f), dx, dy, dz);
+        if (d < 0.0) acc += qd[g.face_nb[f]] * (g.face_rev[f] * (-d));
+    }
+    dst[(size_t)dl * n_periodic + p] = acc;
+}
+
+// incoming_total_rate for every (cell, dir) from the current q (read-back / photon_rate,
+// src/sweep/mod.rs:727-730).  which: 0 incoming (Local faces), 2 periodic_source, 1 outgoing.
+__global__ void __launch_bounds__(256)
+dir_state_kernel(GridView g, const double *__restrict__ q, int which, int n_local_dirs,
+                 double *__restrict__ out_cell_major, double *__restrict__ photon_rate) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.n_cells) return;
+    double total = 0.0;
+    for (int dl = 0; dl < n_local_dirs; ++dl) {
+        const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+        const double *qd = q + (size_t)dl * g.n_cells;
+        double acc = 0.0, ttot = 0.0;
+        for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
+            const double4 geo = ld_geo(g.face_geo + f);
+            const double d = dot_dir(geo, dx, dy, dz);
+            const int kind = g.face_kind[f];
+            if (d < 0.0) {
+                if ((which == 0 && kind == 0) || (which == 2 && kind == 2))
+                    acc += qd[g.face_nb[f]] * (g.face_rev[f] * (-d));
+            } else if (d > 0.0) {
+                ttot += geo.w * d;
+            }
+        }
+        if (which == 1) acc = qd[c] * ttot;
+        if (out_cell_major) out_cell_major[(size_t)c * n_local_dirs + dl] = acc;
+        total += acc;
+    }
+    if (photon_rate) photon_rate[c] = total;
+}
+
+// ------------------------------------------------------------------------------------------
+// rate reduction over this rank's directions: sum_d get_rate(d) (src/sweep/mod.rs:554-558,
+// site.rs:53-56), left fold in direction order.  One thread per active cell; consecutive
+// threads read consecutive cells of incoming[dl][*] (coalesced).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rate_kernel(const uint32_t *__restrict__ act_list, uint32_t n_act, uint32_t n_cells,
+            int n_local_dirs, const double *__restrict__ incoming, const int32_t *__restrict__ pidx,
+            const double *__restrict__ per_new, uint32_t n_periodic, double *__restrict__ rate_act) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_act) return;
+    const uint32_t c = act_list ? act_list[k] : k;
+    const int32_t p = pidx[c];
+    double rate = 0.0;
+    if (p >= 0) {
+        for (int dl = 0; dl < n_local_dirs; ++dl)
+            rate += __ldcs(incoming + (size_t)dl * n_cells + c) + per_new[(size_t)dl * n_periodic + p];
+    } else {
+        for (int dl = 0; dl < n_local_dirs; ++dl) rate += __ldcs(incoming + (size_t)dl * n_cells + c) + 0.0;
+    }
+    rate_act[k] = rate;
+}
+
+// ------------------------------------------------------------------------------------------
+// chemistry: Sweep::update_chemistry (src/sweep/mod.rs:549-574) for one active cell per thread
+// ------------------------------------------------------------------------------------------
+struct ChemParams {
+    double max_timestep, threshold, scale_factor, safety;
+    int prevent_cooling;
+};
+
+struct ChemStats {
+    unsigned long long cells, failures, attempts;
+    unsigned int max_depth;
+};
+
+__global__ void __launch_bounds__(128)
+chemistry_kernel(CellView cv, const uint32_t *__restrict__ act_list, uint32_t n_act,
+                 const double *__restrict__ rate_act, ChemParams cp, ChemStats *stats) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long attempts = 0;
+    unsigned int depth = 0, failed = 0;
+    if (k < n_act) {
+        const uint32_t c = act_list ? act_list[k] : k;
+        const double rate = rate_act[k];
+        const int lvl = cv.level[c];
+        const double timestep = cp.max_timestep * exp2(-(double)lvl);  // max_timestep * 0.5^level (exact)
+        double relative_change;
+        if (fabs(rate) < fabs(cp.threshold)) {                        // chemistry/mod.rs:79-81
+            relative_change = 0.0;
+        } else {                                                      // chemistry/mod.rs:73-77
+            relative_change = fabs(fmin(fabs(fabs(rate - cv.prev_rate[c]) / rate), kInvEps));
+        }
+        cv.prev_rate[c] = rate;
+        const double rate_timescale = timestep / relative_change;
+        Solver s;
+        s.xhii = cv.x[c];
+        s.temperature = cv.T[c];
+        s.density = cv.rho[c];
+        s.volume = cv.volume[c];
+        s.length = cv.size[c];
+        s.rate = rate;
+        s.scale_factor = cp.scale_factor;
+        s.has_floor = cp.prevent_cooling != 0;
+        s.floor_temperature = s.temperature;
+        s.floor_xhii = s.xhii;
+        const ChemResult r = perform_timestep(s, timestep, cp.safety);
+        cv.T[c] = s.temperature;
+        cv.x[c] = s.xhii;
+        cv.ts[c] = r.timescale;
+        cv.tau[c] = (rate_timescale < r.timescale) ? rate_timescale : r.timescale;  // Timescale::min
+        cv.att[c] = non_absorbed_fraction(s.density, s.xhii, s.length);
+        attempts = r.attempts;
+        depth = (unsigned)r.max_depth;
+        failed = (unsigned)r.failed;
+    }
+    // block-level statistics
+    __shared__ unsigned long long s_att, s_fail, s_cells;
+    __shared__ unsigned int s_depth;
+    if (threadIdx.x == 0) { s_att = 0; s_fail = 0; s_cells = 0; s_depth = 0; }
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+        attempts += __shfl_down_sync(0xffffffffu, attempts, o);
+        failed += __shfl_down_sync(0xffffffffu, failed, o);
+        depth = max(depth, __shfl_down_sync(0xffffffffu, depth, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_att, attempts);
+        atomicAdd(&s_fail, (unsigned long long)failed);
+        atomicMax(&s_depth, depth);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t first = blockIdx.x * blockDim.x;
+        const uint32_t n_here = first < n_act ? min(blockDim.x, n_act - first) : 0;
+        atomicAdd(&stats->attempts, s_att);
+        atomicAdd(&stats->failures, s_fail);
+        atomicAdd(&stats->cells, (unsigned long long)n_here);
+        atomicMax(&stats->max_depth, s_depth);
+    }
+}
+
+// att = exp(-n_HI sigma size) for all cells (create / set_inputs)
+__global__ void __launch_bounds__(256) attenuation_kernel(CellView cv, uint32_t n) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) cv.att[c] = non_absorbed_fraction(cv.rho[c], cv.x[c], cv.size[c]);
+}
+
+// ------------------------------------------------------------------------------------------
+// timestep levels: Sweep::update_timestep_levels (src/sweep/mod.rs:576-589),
+// TimestepLevel::from_max_timestep_and_desired_timestep (timestep_level.rs:27-36),
+// get_desired_level_from_desired_timestep (timestep_state.rs:54-64) + per-level histogram
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline int level_rule(int max_num_levels, double max_timestep, double desired) {
+    const double ratio = max_timestep / desired;
+    const double l = ceil(log2(ratio));
+    // Rust `as usize`: NaN -> 0, negative -> 0, huge -> usize::MAX; then clamp(0, L-1)
+    int level;
+    if (!(l > 0.0)) level = 0;
+    else if (l >= (double)(max_num_levels - 1)) level = max_num_levels - 1;
+    else level = (int)l;
+    return level;
+}
+
+__global__ void __launch_bounds__(256)
+levels_kernel(const double *__restrict__ tau, uint8_t *__restrict__ level, uint32_t n, int n_levels,
+              double max_timestep, double safety, int lowest_allowed,
+              unsigned long long *__restrict__ hist /* 32 */) {
+    __shared__ unsigned int s_hist[32];
+    if (threadIdx.x < 32) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) {
+        int lv = level_rule(n_levels, max_timestep, safety * tau[c]);
+        if (lv < lowest_allowed) lv = lowest_allowed;
+        level[c] = (uint8_t)lv;
+        atomicAdd(&s_hist[lv], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256)
+histogram_kernel(const uint8_t *__restrict__ level, uint32_t n, unsigned long long *__restrict__ hist) {
+    __shared__ unsigned int s_hist[32];
+    if (threadIdx.x < 32) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) atomicAdd(&s_hist[level[c] & 31], 1u);
+    __syncthreads();
+    if (threadIdx.x < 32 && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
+}
+
+// ionization_time (src/sweep/mod.rs:731-738): first time xHII > 0.5
+__global__ void __launch_bounds__(256)
+ionization_time_kernel(const double *__restrict__ x, double *__restrict__ ion_time, uint32_t n, double now) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n && x[c] > 0.5 && isnan(ion_time[c])) ion_time[c] = now;
+}
+
+// optional chemistry outputs, src/sweep/chemistry_output.rs:25-55 with Sweep::get_solver (mod.rs:612-632)
+__global__ void __launch_bounds__(256)
+chem_output_kernel(CellView cv, uint32_t n, const double *__restrict__ rate, double scale_factor,
+                   int field, double *__restrict__ out) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    Solver s;
+    s.xhii = cv.x[c];
+    s.temperature = cv.T[c];
+    s.density = cv.rho[c];
+    s.volume = cv.volume[c];
+    s.length = cv.size[c];
+    s.rate = rate[c];
+    s.scale_factor = scale_factor;
+    s.has_floor = false;
+    s.floor_temperature = 0.0;
+    s.floor_xhii = 0.0;
+    const double one_year = 1.0 * units::years;
+    double v;
+    if (field == 5) v = s.photoionization_rate(one_year);
+    else if (field == 6) v = s.photoheating_rate(one_year) - s.cooling_rate();
+    else if (field == 7) v = s.alpha_b() * s.ne() * s.xhii;
+    else v = s.beta() * s.ne() * (1.0 - s.xhii);
+    out[c] = v;
+}
+
+// standalone chemistry on independent cells (ssw_chemistry_batch)
+__global__ void __launch_bounds__(128)
+chemistry_batch_kernel(uint64_t n, double *x, double *T, const double *rho, const double *vol,
+                       const double *len, const double *rate, const double *dt, double scale_factor,
+                       double safety, int prevent_cooling, double *timescale, int *process, int *depth,
+                       unsigned long long *attempts) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Solver s;
+    s.xhii = x[i];
+    s.temperature = T[i];
+    s.density = rho[i];
+    s.volume = vol[i];
+    s.length = len[i];
+    s.rate = rate[i];
+    s.scale_factor = scale_factor;
+    s.has_floor = prevent_cooling != 0;
+    s.floor_temperature = s.temperature;
+    s.floor_xhii = s.xhii;
+    const ChemResult r = perform_timestep(s, dt[i], safety);
+    x[i] = s.xhii;
+    T[i] = s.temperature;
+    timescale[i] = r.timescale;
+    process[i] = r.failed ? -1 : r.process;
+    depth[i] = r.max_depth;
+    attempts[i] = r.attempts;
+}
+
+__global__ void __launch_bounds__(256)
+iota_active_kernel(const uint8_t *__restrict__ level, int cur, uint32_t n, uint8_t *__restrict__ flags) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) flags[c] = level[c] >= cur ? 1 : 0;
+}
+
+
+// sum_d get_rate(d) for every cell from the per-direction sums (Sweep::get_solver, mod.rs:616-620)
+__global__ void __launch_bounds__(256)
+combine_rates_kernel(const double *__restrict__ in_sum, const double *__restrict__ per_sum,
+                     const double *__restrict__ src, double local_dir_fraction, uint32_t n,
+                     double *__restrict__ out) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) out[c] = in_sum[c] + src[c] * local_dir_fraction + per_sum[c];
+}
+
+}  // namespace ssw

@@ -1,0 +1,975 @@
+// sweep.cu -- host side of libsubsweep_b200.so: the B200 mirror of the reference's
+// Sweep<HydrogenOnly> (src/sweep/mod.rs:172-610) and the C ABI of include/subsweep_b200.h.
+//
+// There is no CPU fallback in this file: every path launches the kernels of kernels.cuh /
+// compiled.cuh on the CUDA device and fails with SSW_E_CUDA when that is impossible.
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/subsweep_b200.h"
+#include "kernels.cuh"
+#include "compiled.cuh"
+
+namespace ssw {
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] static void fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    throw Error(code, buf);
+}
+
+#define CUDA_CHECK(expr)                                                                       \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            ::ssw::fail(e__ == cudaErrorMemoryAllocation ? SSW_E_NOMEM : SSW_E_CUDA,           \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+    }
+    void ensure(size_t count) {
+        if (count > n) alloc(count + count / 8);
+    }
+    void upload(const T *src, size_t count, cudaStream_t s) {
+        CUDA_CHECK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void zero(cudaStream_t s) { CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+};
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------
+// wavefront level sets of one active set
+// ------------------------------------------------------------------------------------------
+struct Schedule {
+    bool valid = false;
+    uint64_t version = 0;       // levels_version it was built for
+    uint32_t n_act = 0;
+    uint64_t n_tasks = 0;
+    uint32_t n_levels = 0;
+    DevBuf<uint32_t> act_list;  // ascending cell indices (empty = all cells)
+    DevBuf<uint32_t> tasks;     // level-sorted, (dl, cell)-sorted inside a level
+    DevBuf<uint32_t> level_off; // n_levels + 1
+    std::vector<uint32_t> level_off_host;
+    Compiled compiled;          // slot-ordered form (compiled.cuh), optional
+};
+
+enum TimerCat { T_SWEEP = 0, T_CHEM, T_LEVELS, T_SCHED, T_ALLREDUCE, T_KERNEL, T_COUNT };
+
+struct Sweep {
+    ssw_params P{};
+    std::vector<double> dirs_all;  // D x 3
+    int D = 0, Dl = 0, d0 = 0;
+    uint32_t N = 0;
+    uint64_t F = 0;
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+
+    // grid
+    DevBuf<double4> face_geo;
+    DevBuf<double> face_rev;
+    DevBuf<int32_t> face_nb;
+    DevBuf<uint8_t> face_kind;
+    DevBuf<uint32_t> face_off;
+    DevBuf<double> size, volume;
+    // cells
+    DevBuf<double> rho, x, T, ts, tau, prev_rate, src, att, ion_time;
+    DevBuf<uint8_t> level;
+    DevBuf<int32_t> pidx;
+    DevBuf<uint32_t> pcells;
+    uint32_t n_periodic = 0;
+    // per (dir, cell)
+    DevBuf<double> q, incoming;
+    DevBuf<int32_t> missing;
+    DevBuf<double> per_lag, per_new;
+    // scratch
+    DevBuf<uint32_t> queue_scratch;
+    DevBuf<uint32_t> level_off_scratch;
+    DevBuf<QueueCtl> ctl;
+    DevBuf<uint8_t> flags;
+    DevBuf<uint8_t> cub_temp;
+    DevBuf<uint32_t> n_selected;
+    DevBuf<double> rate_act, cell_tmp, cell_tmp2;
+    DevBuf<unsigned long long> hist;
+    DevBuf<ChemStats> chem_stats;
+    DevBuf<int32_t> wlevel;
+
+    // TimestepState (src/sweep/timestep_state.rs:4-9)
+    int lowest_allowed = 0;
+    bool first_done = false;
+    double sim_time = 0.0;
+    std::vector<uint64_t> bin_count;  // cells per level
+    uint64_t levels_version = 1;
+
+    std::vector<std::unique_ptr<Schedule>> sched;  // [0..L-1] partial sets by current level, [L] all cells
+
+    ssw_allreduce_fn allreduce = nullptr;
+    void *allreduce_ctx = nullptr;
+
+    // statistics / timers
+    uint64_t stat[16] = {0};
+    struct Pending { cudaEvent_t a, b; int cat; int lvl; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> event_pool;
+    ssw_timings timings{};
+    int coop_blocks_build = 0, coop_blocks_replay = 0;
+
+    ~Sweep() {
+        for (auto &p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+        for (auto e : event_pool) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    // ---- helpers ----
+    void bind() {
+        CUDA_CHECK(cudaSetDevice(device));
+        CUDA_CHECK(cudaMemcpyToSymbolAsync(c_dirs, dirs_all.data() + 3 * (size_t)d0,
+                                           sizeof(double) * 3 * (size_t)Dl, 0,
+                                           cudaMemcpyHostToDevice, stream));
+    }
+    void launched(uint64_t n = 1) { stat[SSW_STAT_KERNEL_LAUNCHES] += n; }
+    cudaEvent_t get_event() {
+        if (!event_pool.empty()) {
+            cudaEvent_t e = event_pool.back();
+            event_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        CUDA_CHECK(cudaEventCreate(&e));
+        return e;
+    }
+    size_t tic(int cat, int lvl = -1) {
+        Pending p{get_event(), get_event(), cat, lvl};
+        CUDA_CHECK(cudaEventRecord(p.a, stream));
+        pending.push_back(p);
+        return pending.size() - 1;
+    }
+    void toc(size_t id) { CUDA_CHECK(cudaEventRecord(pending[id].b, stream)); }
+    void resolve_timers() {
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        for (auto &p : pending) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+                switch (p.cat) {
+                case T_SWEEP:
+                    timings.sweep_ms += ms;
+                    if (p.lvl >= 0 && p.lvl < 32) timings.sweep_level_ms[p.lvl] += ms;
+                    break;
+                case T_CHEM: timings.chemistry_ms += ms; break;
+                case T_LEVELS: timings.update_levels_ms += ms; break;
+                case T_SCHED: timings.schedule_ms += ms; break;
+                case T_ALLREDUCE: timings.allreduce_ms += ms; break;
+                case T_KERNEL: timings.sweep_kernel_ms += ms; break;
+                }
+            }
+            event_pool.push_back(p.a);
+            event_pool.push_back(p.b);
+        }
+        pending.clear();
+    }
+
+    GridView grid_view() const {
+        GridView g;
+        g.face_geo = face_geo.p;
+        g.face_rev = face_rev.p;
+        g.face_nb = face_nb.p;
+        g.face_kind = face_kind.p;
+        g.face_off = face_off.p;
+        g.n_cells = N;
+        return g;
+    }
+    CellView cell_view() const {
+        CellView c;
+        c.rho = rho.p; c.x = x.p; c.T = T.p; c.ts = ts.p; c.tau = tau.p;
+        c.prev_rate = prev_rate.p; c.src = src.p; c.att = att.p; c.ion_time = ion_time.p;
+        c.size = size.p; c.volume = volume.p; c.level = level.p; c.pidx = pidx.p;
+        return c;
+    }
+    SweepArgs sweep_args(int cur) const {
+        SweepArgs a;
+        a.g = grid_view();
+        a.att = att.p;
+        a.src = src.p;
+        a.pidx = pidx.p;
+        a.level = level.p;
+        a.q = q.p;
+        a.incoming = incoming.p;
+        a.per_lag = per_lag.p;
+        a.missing = missing.p;
+        a.n_periodic = n_periodic;
+        a.inv_threshold_unused = 0.0;
+        a.threshold = P.significant_rate_threshold_per_s;
+        a.n_dirs_total = (double)D;
+        a.cur = cur;
+        return a;
+    }
+
+    uint64_t count_at_least(int l) const {
+        uint64_t n = 0;
+        for (int k = l; k < P.n_levels; ++k) n += bin_count[k];
+        return n;
+    }
+
+    void create(const ssw_params *p, const ssw_grid *g, const double *density, const double *xhii,
+                const double *temperature, const double *source);
+    void refresh_histogram();
+    void build_active_list(Schedule &S, int cur);
+    void gather_periodic(double *dst);
+    void build_schedule(Schedule &S, int cur, bool solve, int dl_base, int n_dl, int32_t *wl);
+    void single_sweep(int cur);
+    void update_timestep_levels();
+    double run_sweeps();
+    void read_field(int field, double *out);
+    void all_rates(double *dev_out);
+    void maybe_allreduce(double *buf, uint64_t n);
+};
+
+static int coop_grid(const void *kernel, int threads, int num_sms) {
+    int per_sm = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+    if (per_sm < 1) fail(SSW_E_CUDA, "cooperative kernel does not fit on an SM");
+    return per_sm * num_sms;
+}
+
+// ------------------------------------------------------------------------------------------
+// Sweep::new (src/sweep/mod.rs:194-232) + init_sweep_system (:634-692)
+// ------------------------------------------------------------------------------------------
+void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density,
+                   const double *xhii, const double *temperature, const double *source) {
+    if (!p || !g || !density || !xhii || !temperature || !source) fail(SSW_E_INVALID, "null argument");
+    if (p->n_dirs < 1 || p->n_dirs > kMaxDirs || !p->dirs_xyz)
+        fail(SSW_E_INVALID, "n_dirs must be in [1, %d]", kMaxDirs);
+    if (p->n_levels < 1 || p->n_levels > 31)   // timestep_state.rs:72 asserts < 32
+        fail(SSW_E_INVALID, "num_timestep_levels must be in [1, 31]");
+    if (g->n_cells < 1 || g->n_cells > 0xfffffff0ull) fail(SSW_E_INVALID, "bad n_cells");
+    if (p->world_size < 0 || (p->world_size > 1 && (p->rank < 0 || p->rank >= p->world_size)))
+        fail(SSW_E_INVALID, "bad rank / world_size");
+    P = *p;
+    if (P.world_size < 1) { P.world_size = 1; P.rank = 0; }
+    D = p->n_dirs;
+    dirs_all.assign(p->dirs_xyz, p->dirs_xyz + 3 * (size_t)D);
+    P.dirs_xyz = nullptr;
+    int32_t b = 0, e = D;
+    ssw_direction_shard(D, P.world_size, P.rank, &b, &e);
+    d0 = b;
+    Dl = e - b;
+    if (Dl < 1) fail(SSW_E_INVALID, "rank %d of %d has no direction (D = %d)", P.rank, P.world_size, D);
+    N = (uint32_t)g->n_cells;
+    F = g->face_offsets[N];
+    if (F > 0xfffffff0ull) fail(SSW_E_INVALID, "too many faces");
+    if ((uint64_t)N * (uint64_t)Dl > 0xfffffff0ull)
+        fail(SSW_E_INVALID, "n_cells * local directions must be < 2^32");
+
+    // ---- device ----
+    device = p->device_id;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
+        fail(SSW_E_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= n_dev) fail(SSW_E_CUDA, "device %d out of range (%d devices)", device, n_dev);
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) fail(SSW_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    if (!prop.cooperativeLaunch) fail(SSW_E_CUDA, "device lacks cooperative launch");
+    num_sms = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+
+    // ---- validate the grid, find the reverse face of every face ----
+    std::vector<double4> geo(F);
+    std::vector<double> rev(F, 0.0);
+    std::vector<uint32_t> off(N + 1);
+    std::vector<int32_t> pidx_h(N, -1);
+    std::vector<uint32_t> pcells_h;
+    for (uint32_t c = 0; c <= N; ++c) {
+        if (c > 0 && g->face_offsets[c] < g->face_offsets[c - 1]) fail(SSW_E_INVALID, "face_offsets not monotone at cell %u", c);
+        off[c] = (uint32_t)g->face_offsets[c];
+    }
+    if (off[0] != 0) fail(SSW_E_INVALID, "face_offsets[0] must be 0");
+    for (uint32_t c = 0; c < N; ++c) {
+        bool has_periodic = false;
+        for (uint32_t f = off[c]; f < off[c + 1]; ++f) {
+            const double *n = g->face_normal + 3 * (size_t)f;
+            geo[f] = make_double4(n[0], n[1], n[2], g->face_area[f]);
+            const uint8_t kind = g->face_kind[f];
+            const int32_t nb = g->face_neighbour[f];
+            if (kind == SSW_FACE_BOUNDARY) continue;
+            if (kind != SSW_FACE_LOCAL && kind != SSW_FACE_LOCAL_PERIODIC) fail(SSW_E_INVALID, "face %u: bad kind %d", f, (int)kind);
+            if (nb < 0 || (uint32_t)nb >= N) fail(SSW_E_INVALID, "face %u: neighbour %d out of range", f, nb);
+            if (kind == SSW_FACE_LOCAL_PERIODIC) has_periodic = true;
+            // reverse face: the neighbour's face back to c, same kind, most anti-parallel normal
+            double best = 2.0;
+            int64_t bestg = -1;
+            for (uint32_t gg = off[nb]; gg < off[nb + 1]; ++gg) {
+                if (g->face_neighbour[gg] != (int32_t)c || g->face_kind[gg] != kind) continue;
+                const double *m = g->face_normal + 3 * (size_t)gg;
+                const double dd = n[0] * m[0] + n[1] * m[1] + n[2] * m[2];
+                if (dd < best) { best = dd; bestg = gg; }
+            }
+            if (bestg < 0) fail(SSW_E_INVALID, "face %u of cell %u has no reverse face in cell %d", f, c, nb);
+            const double *m = g->face_normal + 3 * (size_t)bestg;
+            if (std::fabs(n[0] + m[0]) > 1e-9 || std::fabs(n[1] + m[1]) > 1e-9 || std::fabs(n[2] + m[2]) > 1e-9)
+                fail(SSW_E_INVALID, "face %u of cell %u: normal is not the negative of its reverse face's", f, c);
+            rev[f] = g->face_area[bestg];
+        }
+        if (has_periodic) {
+            pidx_h[c] = (int32_t)pcells_h.size();
+            pcells_h.push_back(c);
+        }
+    }
+    n_periodic = (uint32_t)pcells_h.size();
+
+    // ---- upload ----
+    face_geo.alloc(F); face_geo.upload(geo.data(), F, stream);
+    face_rev.alloc(F); face_rev.upload(rev.data(), F, stream);
+    face_nb.alloc(F); face_nb.upload(g->face_neighbour, F, stream);
+    face_kind.alloc(F); face_kind.upload(g->face_kind, F, stream);
+    face_off.alloc(N + 1); face_off.upload(off.data(), N + 1, stream);
+    size.alloc(N); size.upload(g->cell_size, N, stream);
+    volume.alloc(N); volume.upload(g->cell_volume, N, stream);
+    rho.alloc(N); rho.upload(density, N, stream);
+    x.alloc(N); x.upload(xhii, N, stream);
+    T.alloc(N); T.upload(temperature, N, stream);
+    src.alloc(N); src.upload(source, N, stream);
+    ts.alloc(N); ts.zero(stream);
+    tau.alloc(N); tau.zero(stream);
+    prev_rate.alloc(N); prev_rate.zero(stream);
+    att.alloc(N);
+    ion_time.alloc(N);
+    {
+        std::vector<double> nanv(N, std::numeric_limits<double>::quiet_NaN());
+        ion_time.upload(nanv.data(), N, stream);
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    pidx.alloc(N); pidx.upload(pidx_h.data(), N, stream);
+    pcells.alloc(n_periodic); if (n_periodic) pcells.upload(pcells_h.data(), n_periodic, stream);
+    level.alloc(N);
+    CUDA_CHECK(cudaMemsetAsync(level.p, P.n_levels - 1, N, stream));  // initial_level, mod.rs:206
+    const size_t ND = (size_t)N * Dl;
+    q.alloc(ND); q.zero(stream);
+    incoming.alloc(ND); incoming.zero(stream);
+    per_lag.alloc((size_t)n_periodic * Dl); per_lag.zero(stream);
+    per_new.alloc((size_t)n_periodic * Dl); per_new.zero(stream);
+    ctl.alloc(1);
+    flags.alloc(N);
+    n_selected.alloc(1);
+    rate_act.alloc(N);
+    cell_tmp.alloc(N);
+    cell_tmp2.alloc(N);
+    hist.alloc(32);
+    chem_stats.alloc(1); chem_stats.zero(stream);
+    CUDA_CHECK(cudaStreamSynchronize(stream));  // host vectors go out of scope
+
+    bind();
+    attenuation_kernel<<<cdiv(N, 256), 256, 0, stream>>>(cell_view(), N);
+    launched();
+    CUDA_CHECK(cudaGetLastError());
+
+    lowest_allowed = P.n_levels - 1;  // timestep_state.rs:17
+    first_done = false;
+    bin_count.assign(P.n_levels, 0);
+    bin_count[P.n_levels - 1] = N;
+    sched.resize(P.n_levels + 1);
+    for (auto &s : sched) s.reset(new Schedule());
+    coop_blocks_build = coop_grid((const void *)sweep_build_kernel, 256, num_sms);
+    coop_blocks_replay = coop_grid((const void *)sweep_replay_kernel, 256, num_sms);
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+void Sweep::refresh_histogram() {
+    hist.zero(stream);
+    histogram_kernel<<<cdiv(N, 256), 256, 0, stream>>>(level.p, N, hist.p);
+    launched();
+    unsigned long long h[32];
+    CUDA_CHECK(cudaMemcpyAsync(h, hist.p, sizeof h, cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    for (int l = 0; l < P.n_levels; ++l) bin_count[l] = h[l];
+    levels_version++;
+}
+
+// ActiveList::enumerate_active (src/sweep/active_list.rs:55-66) as a compacted ascending list
+void Sweep::build_active_list(Schedule &S, int cur) {
+    iota_active_kernel<<<cdiv(N, 256), 256, 0, stream>>>(level.p, cur, N, flags.p);
+    launched();
+    S.act_list.ensure(S.n_act);
+    cub::CountingInputIterator<uint32_t> iota(0);
+    size_t bytes = 0;
+    CUDA_CHECK(cub::DeviceSelect::Flagged(nullptr, bytes, iota, flags.p, S.act_list.p, n_selected.p, (int)N, stream));
+    cub_temp.ensure(bytes);
+    CUDA_CHECK(cub::DeviceSelect::Flagged(cub_temp.p, bytes, iota, flags.p, S.act_list.p, n_selected.p, (int)N, stream));
+    launched(2);
+    uint32_t got = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&got, n_selected.p, sizeof got, cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (got != S.n_act) fail(SSW_E_CUDA, "active list has %u cells, histogram says %u", got, S.n_act);
+}
+
+void Sweep::gather_periodic(double *dst) {
+    if (!n_periodic) return;
+    dim3 grid(cdiv(n_periodic, 256), Dl);
+    periodic_gather_kernel<<<grid, 256, 0, stream>>>(grid_view(), pcells.p, n_periodic, q.p, dst);
+    launched();
+}
+
+// Kahn peeling (+ solve) for the active set of `cur`: init_counts, get_initial_tasks, solve
+// (src/sweep/mod.rs:346-398, 291-314).  The resulting level sets are stored in S.
+void Sweep::build_schedule(Schedule &S, int cur, bool solve, int dl_base, int n_dl, int32_t *wl) {
+    const uint64_t n_tasks = (uint64_t)S.n_act * n_dl;
+    missing.ensure((size_t)N * Dl);
+    queue_scratch.ensure(n_tasks);
+    const uint32_t cap = (uint32_t)std::min<uint64_t>((uint64_t)S.n_act + 2, 1u << 24);
+    level_off_scratch.ensure(cap);
+    CUDA_CHECK(cudaMemsetAsync(ctl.p, 0, sizeof(QueueCtl), stream));
+    const uint32_t *act = S.act_list.n && S.n_act != N ? S.act_list.p : nullptr;
+    {
+        dim3 grid(cdiv(S.n_act, 256), n_dl);
+        init_counts_kernel<<<grid, 256, 0, stream>>>(grid_view(), level.p, cur, act, S.n_act,
+                                                     missing.p, queue_scratch.p, ctl.p, wl, dl_base);
+        launched();
+        CUDA_CHECK(cudaGetLastError());
+    }
+    SweepArgs a = sweep_args(cur);
+    if (!solve) { a.q = nullptr; a.incoming = nullptr; }
+    uint32_t *qp = queue_scratch.p;
+    QueueCtl *cp = ctl.p;
+    uint32_t *lo = level_off_scratch.p;
+    uint32_t lcap = cap;
+    void *args[] = {&a, &qp, &cp, &lo, &lcap, &wl};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)sweep_build_kernel, dim3(coop_blocks_build),
+                                           dim3(256), args, 0, stream));
+    launched();
+    QueueCtl h;
+    CUDA_CHECK(cudaMemcpyAsync(&h, ctl.p, sizeof h, cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (h.overflow) fail(SSW_E_NOMEM, "more than %u wavefront levels", cap);
+    if (h.solved != n_tasks) {
+        if (P.check_deadlock && h.cnt[0] == 0 && h.n_levels == 0)
+            fail(SSW_E_DEADLOCK, "deadlock: no initial task (level %d)", cur);   // deadlock_detection.rs:86-98
+        fail(SSW_E_DEADLOCK, "dependency cycle among active cells: solved %u of %llu tasks at level %d",
+             h.solved, (unsigned long long)n_tasks, cur);
+    }
+    S.n_tasks = n_tasks;
+    S.n_levels = h.n_levels;
+    S.level_off_host.resize(h.n_levels + 1);
+    CUDA_CHECK(cudaMemcpyAsync(S.level_off_host.data(), level_off_scratch.p, sizeof(uint32_t) * (h.n_levels + 1),
+                               cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+void Sweep::maybe_allreduce(double *buf, uint64_t n) {
+    if (P.world_size <= 1) return;  // one direction shard: no collective (north_star)
+    if (!allreduce) fail(SSW_E_COMM, "world_size > 1 but no all-reduce hook set (ssw_set_allreduce)");
+    const size_t t = tic(T_ALLREDUCE);
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (allreduce(allreduce_ctx, buf, n, (void *)stream) != 0) fail(SSW_E_COMM, "all-reduce hook failed");
+    toc(t);
+}
+
+// Sweep::single_sweep (src/sweep/mod.rs:274-289)
+void Sweep::single_sweep(int cur) {
+    const uint64_t n_act64 = count_at_least(cur);
+    if (n_act64 == 0) return;
+    const uint32_t n_act = (uint32_t)n_act64;
+    const bool all = n_act == N;
+    Schedule &S = *sched[all ? P.n_levels : cur];
+    const bool cache_ok = !(P.flags & SSW_FLAG_NO_SCHEDULE_CACHE);
+    const bool reuse = cache_ok && S.valid && S.n_act == n_act && (all || S.version == levels_version);
+    const size_t t_sweep = tic(T_SWEEP, cur);
+
+    // periodic_source as the tasks of this sweep will read it (lagged)
+    gather_periodic(per_lag.p);
+
+    if (!reuse) {
+        const size_t t_sched = tic(T_SCHED);
+        S.valid = false;
+        S.compiled.release();
+        S.n_act = n_act;
+        if (!all) build_active_list(S, cur);
+        const size_t t_k = tic(T_KERNEL);
+        build_schedule(S, cur, /*solve=*/true, 0, Dl, nullptr);
+        toc(t_k);
+        timings.sweep_kernel_launches += 1;
+        timings.sweep_kernel_tasks += S.n_tasks;
+        // keep the level sets: sort every level by (direction, cell) so replays walk memory in order
+        S.tasks.ensure(S.n_tasks);
+        S.level_off.ensure(S.n_levels + 1);
+        CUDA_CHECK(cudaMemcpyAsync(S.level_off.p, level_off_scratch.p, sizeof(uint32_t) * (S.n_levels + 1),
+                                   cudaMemcpyDeviceToDevice, stream));
+        if (cache_ok) {
+            size_t bytes = 0;
+            CUDA_CHECK(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, queue_scratch.p, S.tasks.p,
+                                                          (int64_t)S.n_tasks, (int64_t)S.n_levels,
+                                                          S.level_off.p, S.level_off.p + 1, stream));
+            cub_temp.ensure(bytes);
+            CUDA_CHECK(cub::DeviceSegmentedSort::SortKeys(cub_temp.p, bytes, queue_scratch.p, S.tasks.p,
+                                                          (int64_t)S.n_tasks, (int64_t)S.n_levels,
+                                                          S.level_off.p, S.level_off.p + 1, stream));
+            launched(3);
+            S.valid = true;
+            S.version = levels_version;
+        }
+        stat[SSW_STAT_SCHEDULE_BUILDS]++;
+        toc(t_sched);
+    } else {
+        const bool use_compiled = !(P.flags & SSW_FLAG_NO_COMPILED_PATH) && compiled_supported();
+        if (use_compiled && !S.compiled.valid) {
+            const size_t t_sched = tic(T_SCHED);
+            compile_schedule(S.compiled, grid_view(), S.tasks.p, S.level_off_host, S.n_tasks, S.n_levels,
+                             Dl, pidx.p, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
+            toc(t_sched);
+        }
+        const size_t t_k = tic(T_KERNEL);
+        SweepArgs a = sweep_args(cur);
+        if (use_compiled && S.compiled.valid) {
+            run_compiled(S.compiled, a, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
+        } else {
+            const uint32_t *qp = S.tasks.p;
+            const uint32_t *lo = S.level_off.p;
+            uint32_t nl = S.n_levels;
+            void *args[] = {&a, &qp, &lo, &nl};
+            CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)sweep_replay_kernel, dim3(coop_blocks_replay),
+                                                   dim3(256), args, 0, stream));
+            launched();
+        }
+        toc(t_k);
+        timings.sweep_kernel_launches += 1;
+        timings.sweep_kernel_tasks += S.n_tasks;
+        stat[SSW_STAT_SCHEDULE_REPLAYS]++;
+    }
+    stat[SSW_STAT_TASKS_SOLVED] += S.n_tasks;
+    stat[SSW_STAT_WAVEFRONT_LEVELS] = S.n_levels;
+    toc(t_sweep);
+
+    // update_chemistry (src/sweep/mod.rs:549-574)
+    const size_t t_chem = tic(T_CHEM);
+    gather_periodic(per_new.p);
+    const uint32_t *act = all ? nullptr : S.act_list.p;
+    rate_kernel<<<cdiv(n_act, 256), 256, 0, stream>>>(act, n_act, N, Dl, incoming.p, pidx.p, per_new.p,
+                                                      n_periodic, rate_act.p);
+    launched();
+    maybe_allreduce(rate_act.p, n_act);
+    ChemParams cp;
+    cp.max_timestep = P.max_timestep_s;
+    cp.threshold = P.significant_rate_threshold_per_s;
+    cp.scale_factor = P.scale_factor;
+    cp.safety = P.chemistry_timestep_safety_factor;
+    cp.prevent_cooling = P.prevent_cooling;
+    chemistry_kernel<<<cdiv(n_act, 128), 128, 0, stream>>>(cell_view(), act, n_act, rate_act.p, cp, chem_stats.p);
+    launched();
+    CUDA_CHECK(cudaGetLastError());
+    toc(t_chem);
+    stat[SSW_STAT_SINGLE_SWEEPS]++;
+}
+
+// Sweep::update_timestep_levels (src/sweep/mod.rs:576-589)
+void Sweep::update_timestep_levels() {
+    const size_t t = tic(T_LEVELS);
+    hist.zero(stream);
+    levels_kernel<<<cdiv(N, 256), 256, 0, stream>>>(tau.p, level.p, N, P.n_levels, P.max_timestep_s,
+                                                    P.timestep_safety_factor, lowest_allowed, hist.p);
+    launched();
+    unsigned long long h[32];
+    CUDA_CHECK(cudaMemcpyAsync(h, hist.p, sizeof h, cudaMemcpyDeviceToHost, stream));
+    toc(t);
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    for (int l = 0; l < P.n_levels; ++l) bin_count[l] = h[l];
+    levels_version++;
+}
+
+// Sweep::run_sweeps (src/sweep/mod.rs:258-272)
+double Sweep::run_sweeps() {
+    bind();
+    std::vector<uint64_t> counts(P.n_levels);
+    for (int l = 0; l < P.n_levels; ++l) counts[l] = count_at_least(l);   // :240-245
+    std::vector<int32_t> order(1u << (P.n_levels - lowest_allowed - 1));
+    const int n = ssw_levels_in_sweep_order(P.n_levels, lowest_allowed, order.data(), (int)order.size());
+    for (int i = 0; i < n; ++i)
+        if (counts[order[i]] > 0) single_sweep(order[i]);
+    const double elapsed = P.max_timestep_s * std::ldexp(1.0, -lowest_allowed);  // timestep_state.rs:77-79
+    if (first_done && lowest_allowed > 0) lowest_allowed -= 1;                   // :37-48
+    first_done = true;
+    update_timestep_levels();
+    sim_time += elapsed;
+    ionization_time_kernel<<<cdiv(N, 256), 256, 0, stream>>>(x.p, ion_time.p, N, sim_time);
+    launched();
+    // fold the chemistry statistics
+    ChemStats cs;
+    CUDA_CHECK(cudaMemcpyAsync(&cs, chem_stats.p, sizeof cs, cudaMemcpyDeviceToHost, stream));
+    resolve_timers();
+    stat[SSW_STAT_CHEM_CELLS] = cs.cells;
+    stat[SSW_STAT_CHEM_FAILURES] = cs.failures;
+    stat[SSW_STAT_CHEM_ATTEMPTS] = cs.attempts;
+    stat[SSW_STAT_CHEM_MAX_DEPTH] = cs.max_depth;
+    return elapsed;
+}
+
+// sum_d get_rate(d) for every cell (Sweep::get_solver, src/sweep/mod.rs:616-620)
+void Sweep::all_rates(double *dev_out) {
+    dir_state_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), q.p, 0, Dl, nullptr, cell_tmp.p);
+    dir_state_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), q.p, 2, Dl, nullptr, cell_tmp2.p);
+    launched(2);
+    const double frac = (double)Dl / (double)D;
+    combine_rates_kernel<<<cdiv(N, 256), 256, 0, stream>>>(cell_tmp.p, cell_tmp2.p, src.p, frac, N, dev_out);
+    launched();
+    maybe_allreduce(dev_out, N);
+}
+
+void Sweep::read_field(int field, double *out) {
+    bind();
+    const double *srcp = nullptr;
+    switch (field) {
+    case SSW_F_XHII: srcp = x.p; break;
+    case SSW_F_TEMPERATURE: srcp = T.p; break;
+    case SSW_F_TIMESTEP: srcp = ts.p; break;
+    case SSW_F_CHANGE_TIMESCALE: srcp = tau.p; break;
+    case SSW_F_PREVIOUS_RATE: srcp = prev_rate.p; break;
+    case SSW_F_DENSITY: srcp = rho.p; break;
+    case SSW_F_SOURCE: srcp = src.p; break;
+    case SSW_F_IONIZATION_TIME: srcp = ion_time.p; break;
+    case SSW_F_PHOTON_RATE:
+        dir_state_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), q.p, 0, Dl, nullptr, cell_tmp.p);
+        launched();
+        maybe_allreduce(cell_tmp.p, N);
+        srcp = cell_tmp.p;
+        break;
+    case SSW_F_PHOTOIONIZATION_RATE:
+    case SSW_F_HEATING_RATE:
+    case SSW_F_RECOMBINATION_RATE:
+    case SSW_F_COLLISIONAL_IONIZATION_RATE:
+        all_rates(rate_act.p);
+        chem_output_kernel<<<cdiv(N, 256), 256, 0, stream>>>(cell_view(), N, rate_act.p, P.scale_factor, field, cell_tmp.p);
+        launched();
+        srcp = cell_tmp.p;
+        break;
+    default: fail(SSW_E_INVALID, "unknown field %d", field);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(out, srcp, sizeof(double) * N, cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+}  // namespace ssw
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+struct ssw_handle {
+    ssw::Sweep s;
+};
+
+#define SSW_TRY try {
+#define SSW_CATCH                                        \
+    }                                                    \
+    catch (const ssw::Error &e) {                        \
+        ssw::g_last_error = e.what();                    \
+        return e.code;                                   \
+    }                                                    \
+    catch (const std::bad_alloc &) {                     \
+        ssw::g_last_error = "host out of memory";        \
+        return SSW_E_NOMEM;                              \
+    }                                                    \
+    catch (const std::exception &e) {                    \
+        ssw::g_last_error = e.what();                    \
+        return SSW_E_INVALID;                            \
+    }                                                    \
+    return SSW_OK;
+
+#define REQUIRE_HANDLE(h) \
+    if (!(h)) ssw::fail(SSW_E_INVALID, "null handle")
+
+extern "C" {
+
+const char *ssw_last_error(void) { return ssw::g_last_error.c_str(); }
+int32_t ssw_abi_version(void) { return SSW_ABI_VERSION; }
+
+int ssw_create(const ssw_params *params, const ssw_grid *grid, const double *density,
+               const double *xhii, const double *temperature, const double *source,
+               ssw_handle **out) {
+    SSW_TRY
+    if (!out) ssw::fail(SSW_E_INVALID, "null out pointer");
+    *out = nullptr;
+    std::unique_ptr<ssw_handle> h(new ssw_handle());
+    h->s.create(params, grid, density, xhii, temperature, source);
+    *out = h.release();
+    SSW_CATCH
+}
+
+void ssw_destroy(ssw_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->s.device);
+    if (h->s.stream) cudaStreamSynchronize(h->s.stream);
+    delete h;
+}
+
+int ssw_set_allreduce(ssw_handle *h, ssw_allreduce_fn fn, void *ctx) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    h->s.allreduce = fn;
+    h->s.allreduce_ctx = ctx;
+    SSW_CATCH
+}
+
+int ssw_run_sweeps(ssw_handle *h, double *time_elapsed_s) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    const double e = h->s.run_sweeps();
+    if (time_elapsed_s) *time_elapsed_s = e;
+    SSW_CATCH
+}
+
+int ssw_set_inputs(ssw_handle *h, const double *density, const double *source) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    auto &s = h->s;
+    s.bind();
+    if (density) s.rho.upload(density, s.N, s.stream);
+    if (source) s.src.upload(source, s.N, s.stream);
+    if (density) {
+        ssw::attenuation_kernel<<<ssw::cdiv(s.N, 256), 256, 0, s.stream>>>(s.cell_view(), s.N);
+        s.launched();
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    SSW_CATCH
+}
+
+int ssw_read(ssw_handle *h, ssw_field field, double *out) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    if (!out) ssw::fail(SSW_E_INVALID, "null out pointer");
+    h->s.read_field((int)field, out);
+    h->s.resolve_timers();
+    SSW_CATCH
+}
+
+int ssw_read_levels(ssw_handle *h, uint8_t *out) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    auto &s = h->s;
+    CUDA_CHECK(cudaSetDevice(s.device));
+    CUDA_CHECK(cudaMemcpyAsync(out, s.level.p, s.N, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    SSW_CATCH
+}
+
+int ssw_level_counts(ssw_handle *h, uint64_t *out) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    for (int l = 0; l < h->s.P.n_levels; ++l) out[l] = h->s.count_at_least(l);
+    SSW_CATCH
+}
+
+int ssw_lowest_allowed_level(ssw_handle *h, int32_t *out) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    *out = h->s.lowest_allowed;
+    SSW_CATCH
+}
+
+int ssw_single_sweep(ssw_handle *h, int32_t level) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    auto &s = h->s;
+    if (level < 0 || level >= s.P.n_levels) ssw::fail(SSW_E_INVALID, "level out of range");
+    s.bind();
+    s.single_sweep(level);
+    ssw::ChemStats cs;
+    CUDA_CHECK(cudaMemcpyAsync(&cs, s.chem_stats.p, sizeof cs, cudaMemcpyDeviceToHost, s.stream));
+    s.resolve_timers();
+    s.stat[SSW_STAT_CHEM_CELLS] = cs.cells;
+    s.stat[SSW_STAT_CHEM_FAILURES] = cs.failures;
+    s.stat[SSW_STAT_CHEM_ATTEMPTS] = cs.attempts;
+    s.stat[SSW_STAT_CHEM_MAX_DEPTH] = cs.max_depth;
+    SSW_CATCH
+}
+
+int ssw_set_levels(ssw_handle *h, const uint8_t *levels) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    auto &s = h->s;
+    for (uint32_t c = 0; c < s.N; ++c)
+        if (levels[c] >= s.P.n_levels) ssw::fail(SSW_E_INVALID, "level %d of cell %u out of range", (int)levels[c], c);
+    s.bind();
+    s.level.upload(levels, s.N, s.stream);
+    s.refresh_histogram();
+    SSW_CATCH
+}
+
+int ssw_set_change_timescale(ssw_handle *h, const double *tau) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    auto &s = h->s;
+    CUDA_CHECK(cudaSetDevice(s.device));
+    s.tau.upload(tau, s.N, s.stream);
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    SSW_CATCH
+}
+
+int ssw_update_timestep_levels(ssw_handle *h) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    h->s.bind();
+    h->s.update_timestep_levels();
+    h->s.resolve_timers();
+    SSW_CATCH
+}
+
+int ssw_read_dir_state(ssw_handle *h, int32_t which, double *out) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    auto &s = h->s;
+    if (which < 0 || which > 2) ssw::fail(SSW_E_INVALID, "which must be 0, 1 or 2");
+    s.bind();
+    ssw::DevBuf<double> tmp;
+    tmp.alloc((size_t)s.N * s.Dl);
+    ssw::dir_state_kernel<<<ssw::cdiv(s.N, 256), 256, 0, s.stream>>>(s.grid_view(), s.q.p, which, s.Dl, tmp.p, nullptr);
+    s.launched();
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(out, tmp.p, sizeof(double) * (size_t)s.N * s.Dl, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    SSW_CATCH
+}
+
+int ssw_read_wavefront_levels(ssw_handle *h, int32_t level, int32_t dir, int32_t *out) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    auto &s = h->s;
+    if (level < 0 || level >= s.P.n_levels) ssw::fail(SSW_E_INVALID, "level out of range");
+    if (dir < s.d0 || dir >= s.d0 + s.Dl) ssw::fail(SSW_E_INVALID, "direction %d is not in this rank's shard [%d, %d)", dir, s.d0, s.d0 + s.Dl);
+    s.bind();
+    ssw::Schedule tmp;
+    tmp.n_act = (uint32_t)s.count_at_least(level);
+    s.wlevel.ensure(s.N);
+    CUDA_CHECK(cudaMemsetAsync(s.wlevel.p, 0xff, sizeof(int32_t) * s.N, s.stream));
+    if (tmp.n_act > 0) {
+        if (tmp.n_act != s.N) s.build_active_list(tmp, level);
+        s.build_schedule(tmp, level, /*solve=*/false, dir - s.d0, 1, s.wlevel.p);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(out, s.wlevel.p, sizeof(int32_t) * s.N, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    SSW_CATCH
+}
+
+int ssw_get_stat(ssw_handle *h, ssw_stat which, uint64_t *out) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    if ((int)which < 0 || (int)which >= 16) ssw::fail(SSW_E_INVALID, "unknown stat");
+    *out = h->s.stat[which];
+    SSW_CATCH
+}
+
+int ssw_get_timings(ssw_handle *h, ssw_timings *out) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    *out = h->s.timings;
+    SSW_CATCH
+}
+
+int ssw_reset_timings(ssw_handle *h) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    std::memset(&h->s.timings, 0, sizeof(ssw_timings));
+    SSW_CATCH
+}
+
+int ssw_direction_shard(int32_t n_dirs, int32_t world_size, int32_t rank, int32_t *begin, int32_t *end) {
+    if (world_size < 1 || rank < 0 || rank >= world_size || n_dirs < 0 || !begin || !end) return SSW_E_INVALID;
+    *begin = (int32_t)((int64_t)n_dirs * rank / world_size);
+    *end = (int32_t)((int64_t)n_dirs * (rank + 1) / world_size);
+    return SSW_OK;
+}
+
+int32_t ssw_level_from_timesteps(int32_t max_num_levels, double max_timestep, double desired) {
+    return ssw::level_rule(max_num_levels, max_timestep, desired);
+}
+
+int32_t ssw_levels_in_sweep_order(int32_t max_num_levels, int32_t lowest_allowed, int32_t *out, int32_t cap) {
+    // TimestepState::iter_levels_in_sweep_order + lowest_active_from_iteration
+    // (src/sweep/timestep_state.rs:22-27, 66-75)
+    const int num = max_num_levels - lowest_allowed;
+    if (num < 1 || num > 31) return 0;
+    const uint32_t count = 1u << (num - 1);
+    int n = 0;
+    for (uint32_t i = 0; i < count; ++i) {
+        int first_bit = num - 1;
+        for (int b = 0; b < 32; ++b)
+            if (i & (1u << b)) { first_bit = b; break; }
+        if (n < cap) out[n] = lowest_allowed + (num - 1 - first_bit);
+        ++n;
+    }
+    return n;
+}
+
+int ssw_chemistry_batch(int32_t device_id, uint64_t n, double *xhii, double *temperature,
+                        const double *density, const double *volume, const double *length,
+                        const double *rate, const double *timestep, double scale_factor,
+                        double safety_factor, int32_t prevent_cooling, double *timescale_out,
+                        int32_t *process_out, int32_t *depth_out, uint64_t *attempts_out) {
+    SSW_TRY
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
+        ssw::fail(SSW_E_CUDA, "no CUDA device: this library has no CPU fallback");
+    CUDA_CHECK(cudaSetDevice(device_id));
+    ssw::DevBuf<double> dx, dT, drho, dvol, dlen, drate, ddt, dts;
+    ssw::DevBuf<int> dproc, ddepth;
+    ssw::DevBuf<unsigned long long> datt;
+    cudaStream_t st = nullptr;
+    dx.alloc(n); dT.alloc(n); drho.alloc(n); dvol.alloc(n); dlen.alloc(n); drate.alloc(n); ddt.alloc(n);
+    dts.alloc(n); dproc.alloc(n); ddepth.alloc(n); datt.alloc(n);
+    dx.upload(xhii, n, st); dT.upload(temperature, n, st); drho.upload(density, n, st);
+    dvol.upload(volume, n, st); dlen.upload(length, n, st); drate.upload(rate, n, st); ddt.upload(timestep, n, st);
+    ssw::chemistry_batch_kernel<<<ssw::cdiv(n, 128), 128, 0, st>>>(n, dx.p, dT.p, drho.p, dvol.p, dlen.p, drate.p, ddt.p,
+                                                                   scale_factor, safety_factor, prevent_cooling,
+                                                                   dts.p, dproc.p, ddepth.p, datt.p);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpy(xhii, dx.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(temperature, dT.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (timescale_out) CUDA_CHECK(cudaMemcpy(timescale_out, dts.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (process_out) CUDA_CHECK(cudaMemcpy(process_out, dproc.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (depth_out) CUDA_CHECK(cudaMemcpy(depth_out, ddepth.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (attempts_out) CUDA_CHECK(cudaMemcpy(attempts_out, datt.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    SSW_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,68 @@
+"""torch.distributed plumbing for direction sharding (one process per GPU).
+
+The library sweeps this rank's shard of the directions and hands the per-cell partial rates to an
+all-reduce hook (``ssw_set_allreduce``).  This module provides that hook on top of
+``torch.distributed`` -- NCCL over NVLink on the GPU box, gloo in the CPU tests.  With one rank
+there is no collective (north_star).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+
+class _CudaBuffer:
+    """Zero-copy view of a device pointer for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def tensor_from_pointer(ptr: int, n: int, device):
+    import torch
+    device = torch.device(device)
+    if device.type == "cuda":
+        return torch.as_tensor(_CudaBuffer(ptr, n), device=device)
+    buf = (ctypes.c_double * n).from_address(ptr)
+    return torch.from_numpy(np.ctypeslib.as_array(buf))
+
+
+def make_allreduce(device, group=None):
+    """Returns ``fn(ptr, n, stream)`` summing ``n`` f64 at ``ptr`` in place over the process group."""
+    import torch
+    import torch.distributed as dist
+
+    device = torch.device(device)
+
+    def allreduce(ptr: int, n: int, stream) -> None:
+        t = tensor_from_pointer(ptr, n, device)
+        if device.type == "cuda":
+            # the library has synchronised its stream before calling the hook
+            with torch.cuda.device(device):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                torch.cuda.current_stream(device).synchronize()
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+    return allreduce
+
+
+def init_from_env(backend: str | None = None):
+    """Initialise torch.distributed from torchrun's environment; returns (rank, world, local_rank)."""
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29531")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local_rank

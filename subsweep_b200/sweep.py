@@ -1,0 +1,314 @@
+"""Host-side mirror of the reference's sweep plugin surface, on top of the C ABI.
+
+Names follow the reference: ``SweepParameters`` (src/sweep/parameters.rs:8-46, the ``sweep:`` YAML
+section), ``Directions`` (src/sweep/direction/mod.rs:36-109), ``Sweep`` with ``run_sweeps``
+(src/sweep/mod.rs:172-272) and the ``init_sweep_system`` / ``run_sweep_system`` pair
+(:634-739) operating on a dict of per-particle component arrays.
+
+Everything numerical happens in libsubsweep_b200.so (CUDA); this file only marshals arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Callable, Optional, Sequence, Union
+
+import numpy as np
+
+from . import capi
+from .grid import FlatGrid
+from .units import parse_quantity
+
+_DATA = Path(__file__).resolve().parent / "data" / "direction_bins.json"
+
+
+class Directions:
+    """Direction bins: hard-coded tables for 1/16/21/32/64/84 (not re-normalised) or explicit,
+    normalised lists (src/sweep/direction/mod.rs:58-109)."""
+
+    def __init__(self, xyz: np.ndarray):
+        self.xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+
+    @classmethod
+    def from_num(cls, num: int) -> "Directions":
+        tables = json.loads(_DATA.read_text())
+        if str(num) not in tables:
+            raise NotImplementedError(f"no direction table for {num} directions")  # unimplemented!() :67
+        return cls(np.array(tables[str(num)], dtype=np.float64))
+
+    @classmethod
+    def explicit(cls, vectors: Sequence[Sequence[float]]) -> "Directions":
+        v = np.array(vectors, dtype=np.float64).reshape(-1, 3)
+        length = np.sqrt(v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1] + v[:, 2] * v[:, 2])
+        return cls(v * (1.0 / length)[:, None])
+
+    @classmethod
+    def from_spec(cls, spec: Union[int, Sequence]) -> "Directions":
+        return cls.from_num(spec) if isinstance(spec, int) else cls.explicit(spec)
+
+    def __len__(self) -> int:
+        return len(self.xyz)
+
+
+@dataclass
+class SweepParameters:
+    """The ``sweep:`` parameter section, same keys and defaults as src/sweep/parameters.rs."""
+    directions: Union[int, Sequence] = 84
+    num_timestep_levels: int = 1
+    periodic: bool = False
+    max_timestep: float = 1.0                      # s
+    rotate_directions: bool = False
+    significant_rate_threshold: float = 0.0        # 1/s
+    timestep_safety_factor: float = 0.1
+    chemistry_timestep_safety_factor: float = 0.1
+    check_deadlock: bool = False
+    prevent_cooling: bool = True
+    num_tasks_to_solve_before_send_receive: int = 10000   # accepted, unused (no MPI messages)
+
+    _KEYS = ("directions", "num_timestep_levels", "periodic", "max_timestep", "rotate_directions",
+             "significant_rate_threshold", "timestep_safety_factor", "chemistry_timestep_safety_factor",
+             "check_deadlock", "prevent_cooling", "num_tasks_to_solve_before_send_receive")
+
+    @classmethod
+    def from_dict(cls, section: dict) -> "SweepParameters":
+        unknown = set(section) - set(cls._KEYS)
+        if unknown:   # serde deny_unknown_fields
+            raise ValueError(f"unknown field(s) in sweep section: {sorted(unknown)}")
+        for required in ("directions", "num_timestep_levels", "periodic", "max_timestep"):
+            if required not in section:
+                raise ValueError(f"missing field `{required}` in sweep section")
+        kw = dict(section)
+        for q in ("max_timestep", "significant_rate_threshold", "timestep_safety_factor",
+                  "chemistry_timestep_safety_factor"):
+            if q in kw:
+                kw[q] = parse_quantity(kw[q])
+        return cls(**kw)
+
+    @classmethod
+    def from_yaml(cls, text: str) -> "SweepParameters":
+        import yaml
+        return cls.from_dict(yaml.safe_load(text)["sweep"])
+
+
+AllReduce = Callable[[int, int, Optional[int]], None]   # (pointer, n_doubles, stream) -> in-place sum
+
+
+def direction_shard(n_dirs: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous direction shard [begin, end) of ``rank`` (ssw_direction_shard)."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError("bad rank / world_size")
+    return n_dirs * rank // world_size, n_dirs * (rank + 1) // world_size
+
+
+class Sweep:
+    """``Sweep<HydrogenOnly>`` behind the C ABI (src/sweep/mod.rs:172-272)."""
+
+    def __init__(self, parameters: SweepParameters, grid: FlatGrid, density, ionized_hydrogen_fraction,
+                 temperature, source, scale_factor: float = 1.0, device_id: int = 0, rank: int = 0,
+                 world_size: int = 1, allreduce: Optional[AllReduce] = None, flags: int = 0, lib=None):
+        if parameters.rotate_directions:
+            raise NotImplementedError("rotate_directions is not supported yet (DESIGN.md, out of scope)")
+        self.lib = lib if lib is not None else capi.load()
+        self.parameters = parameters
+        self.grid = grid
+        self.directions = Directions.from_spec(parameters.directions)
+        self.rank, self.world_size = rank, world_size
+        self.dir_begin, self.dir_end = direction_shard(len(self.directions), world_size, rank)
+        N = grid.n_cells
+        self.n_cells = N
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in
+                (density, ionized_hydrogen_fraction, temperature, source)]
+        for a in arrs:
+            if a.shape != (N,):
+                raise ValueError("per-cell arrays must have shape (n_cells,)")
+        p = capi.Params()
+        p.n_dirs = len(self.directions)
+        p.dirs_xyz = capi.dptr(self.directions.xyz)
+        p.n_levels = parameters.num_timestep_levels
+        p.max_timestep_s = parameters.max_timestep
+        p.timestep_safety_factor = parameters.timestep_safety_factor
+        p.chemistry_timestep_safety_factor = parameters.chemistry_timestep_safety_factor
+        p.significant_rate_threshold_per_s = parameters.significant_rate_threshold
+        p.prevent_cooling = int(parameters.prevent_cooling)
+        p.scale_factor = scale_factor
+        p.check_deadlock = int(parameters.check_deadlock)
+        p.device_id = device_id
+        p.rank, p.world_size = rank, world_size
+        p.flags = flags
+        g = capi.Grid()
+        g.n_cells = N
+        self._keep = (np.ascontiguousarray(grid.face_offsets, dtype=np.uint64),
+                      np.ascontiguousarray(grid.face_area, dtype=np.float64),
+                      np.ascontiguousarray(grid.face_normal, dtype=np.float64),
+                      np.ascontiguousarray(grid.face_neighbour, dtype=np.int32),
+                      np.ascontiguousarray(grid.face_kind, dtype=np.uint8),
+                      np.ascontiguousarray(grid.cell_size, dtype=np.float64),
+                      np.ascontiguousarray(grid.cell_volume, dtype=np.float64))
+        fo, fa, fn, fnb, fk, cs, cv = self._keep
+        g.face_offsets = fo.ctypes.data_as(C.POINTER(C.c_uint64))
+        g.face_area = capi.dptr(fa)
+        g.face_normal = capi.dptr(fn)
+        g.face_neighbour = fnb.ctypes.data_as(C.POINTER(C.c_int32))
+        g.face_kind = fk.ctypes.data_as(C.POINTER(C.c_uint8))
+        g.cell_size = capi.dptr(cs)
+        g.cell_volume = capi.dptr(cv)
+        self._h = C.c_void_p()
+        self._check(self.lib.ssw_create(C.byref(p), C.byref(g), *(capi.dptr(a) for a in arrs), C.byref(self._h)))
+        self._cb = None
+        if world_size > 1:
+            if allreduce is None:
+                raise ValueError("world_size > 1 needs an allreduce callable")
+            self.set_allreduce(allreduce)
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise capi.SubsweepError(rc, (self.lib.ssw_last_error() or b"").decode())
+
+    def set_allreduce(self, fn: AllReduce) -> None:
+        def trampoline(_ctx, buf, n, stream):
+            try:
+                fn(int(buf), int(n), int(stream) if stream else None)
+                return 0
+            except Exception as exc:  # must not propagate through C
+                import sys
+                print(f"subsweep_b200: allreduce hook failed: {exc!r}", file=sys.stderr)
+                return -1
+        self._cb = capi.ALLREDUCE_FN(trampoline)
+        self._check(self.lib.ssw_set_allreduce(self._h, self._cb, None))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.ssw_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- the hot path --------------------------------------------------------------------------
+    def run_sweeps(self) -> float:
+        """Sweep::run_sweeps: one full step; returns the elapsed simulation time in s."""
+        t = C.c_double()
+        self._check(self.lib.ssw_run_sweeps(self._h, C.byref(t)))
+        return t.value
+
+    def single_sweep(self, level: int) -> None:
+        self._check(self.lib.ssw_single_sweep(self._h, level))
+
+    def update_timestep_levels(self) -> None:
+        self._check(self.lib.ssw_update_timestep_levels(self._h))
+
+    def set_inputs(self, density=None, source=None) -> None:
+        d = None if density is None else np.ascontiguousarray(density, dtype=np.float64)
+        s = None if source is None else np.ascontiguousarray(source, dtype=np.float64)
+        self._check(self.lib.ssw_set_inputs(self._h, capi.dptr(d) if d is not None else None,
+                                            capi.dptr(s) if s is not None else None))
+
+    # -- read-back -------------------------------------------------------------------------------
+    def read(self, field_name: str, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.n_cells)
+        self._check(self.lib.ssw_read(self._h, capi.FIELDS[field_name], capi.dptr(out)))
+        return out
+
+    def levels(self) -> np.ndarray:
+        out = np.empty(self.n_cells, dtype=np.uint8)
+        self._check(self.lib.ssw_read_levels(self._h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def level_counts(self) -> np.ndarray:
+        out = np.zeros(self.parameters.num_timestep_levels, dtype=np.uint64)
+        self._check(self.lib.ssw_level_counts(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def lowest_allowed_level(self) -> int:
+        v = C.c_int32()
+        self._check(self.lib.ssw_lowest_allowed_level(self._h, C.byref(v)))
+        return v.value
+
+    def set_levels(self, levels) -> None:
+        lv = np.ascontiguousarray(levels, dtype=np.uint8)
+        self._check(self.lib.ssw_set_levels(self._h, lv.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+    def set_change_timescale(self, tau) -> None:
+        t = np.ascontiguousarray(tau, dtype=np.float64)
+        self._check(self.lib.ssw_set_change_timescale(self._h, capi.dptr(t)))
+
+    def dir_state(self, which: str) -> np.ndarray:
+        idx = {"incoming": 0, "outgoing": 1, "periodic": 2}[which]
+        out = np.empty((self.n_cells, self.dir_end - self.dir_begin))
+        self._check(self.lib.ssw_read_dir_state(self._h, idx, capi.dptr(out)))
+        return out
+
+    def wavefront_levels(self, level: int, direction: int) -> np.ndarray:
+        out = np.empty(self.n_cells, dtype=np.int32)
+        self._check(self.lib.ssw_read_wavefront_levels(self._h, level, direction,
+                                                       out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def stat(self, name: str) -> int:
+        v = C.c_uint64()
+        self._check(self.lib.ssw_get_stat(self._h, capi.STATS[name], C.byref(v)))
+        return v.value
+
+    def timings(self) -> dict:
+        t = capi.Timings()
+        self._check(self.lib.ssw_get_timings(self._h, C.byref(t)))
+        return t.as_dict()
+
+    def reset_timings(self) -> None:
+        self._check(self.lib.ssw_reset_timings(self._h))
+
+
+# ---------------------------------------------------------------------------------------------
+# the two bevy systems of SweepPlugin, on a dict of per-particle component arrays
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class SweepPlugin:
+    """``SweepPlugin`` (src/sweep/mod.rs:111-169): init in StartupStages::InitSweep, one
+    ``run_sweep_system`` per update.  ``components`` maps the reference's snapshot field names
+    (src/components.rs:14-83) to numpy arrays in ParticleId.index order."""
+    parameters: SweepParameters
+    scale_factor: float = 1.0
+    device_id: int = 0
+    rank: int = 0
+    world_size: int = 1
+    allreduce: Optional[AllReduce] = None
+    solver: Optional[Sweep] = field(default=None, init=False)
+    is_first_time: bool = field(default=True, init=False)
+    simulation_time: float = field(default=0.0, init=False)
+
+    def init_sweep_system(self, grid: FlatGrid, components: dict) -> None:
+        self.solver = Sweep(self.parameters, grid, components["density"],
+                            components["ionized_hydrogen_fraction"], components["temperature"],
+                            components["source"], scale_factor=self.scale_factor,
+                            device_id=self.device_id, rank=self.rank, world_size=self.world_size,
+                            allreduce=self.allreduce)
+        n = grid.n_cells
+        components.setdefault("photon_rate", np.zeros(n))
+        components.setdefault("timestep", np.zeros(n))
+        components.setdefault("ionization_time", np.full(n, np.nan))
+
+    def run_sweep_system(self, components: dict) -> None:
+        # the first call is a no-op so that the initial conditions get written (mod.rs:711-714)
+        if self.is_first_time:
+            self.is_first_time = False
+            return
+        s = self.solver
+        self.simulation_time += s.run_sweeps()
+        s.read("ionized_hydrogen_fraction", components["ionized_hydrogen_fraction"])
+        s.read("temperature", components["temperature"])
+        s.read("timestep", components["timestep"])
+        s.read("photon_rate", components["photon_rate"])
+        s.read("ionization_time", components["ionization_time"])

@@ -1,0 +1,146 @@
+"""Host-side logic that needs no GPU: parameter section, directions, sharding, scheduling rules
+exported by the C ABI (pure host functions of libsubsweep_b200.so)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from subsweep_b200 import Directions, SweepParameters, capi, direction_shard
+from subsweep_b200 import units as U
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_sweep_parameters_defaults_and_units():
+    p = SweepParameters.from_yaml("""
+sweep:
+  directions: 84
+  num_timestep_levels: 4
+  periodic: true
+  max_timestep: 1 Myr
+  significant_rate_threshold: 1.0e-5 s^-1
+""")
+    assert p.directions == 84 and p.num_timestep_levels == 4 and p.periodic
+    assert p.max_timestep == 1e6 * 3.15576e7
+    assert p.significant_rate_threshold == 1e-5
+    # defaults of src/sweep/parameters.rs:64-78
+    assert p.timestep_safety_factor == 0.1 and p.chemistry_timestep_safety_factor == 0.1
+    assert p.prevent_cooling is True and p.rotate_directions is False and p.check_deadlock is False
+    assert p.num_tasks_to_solve_before_send_receive == 10000
+
+
+def test_sweep_parameters_deny_unknown_fields():
+    with pytest.raises(ValueError, match="unknown field"):
+        SweepParameters.from_dict(dict(directions=1, num_timestep_levels=1, periodic=False,
+                                       max_timestep="1 s", bogus=3))
+    with pytest.raises(ValueError, match="missing field"):
+        SweepParameters.from_dict(dict(directions=1, num_timestep_levels=1, periodic=False))
+
+
+def test_direction_tables():
+    for n in (1, 16, 21, 32, 64, 84):
+        d = Directions.from_num(n)
+        assert d.xyz.shape == (n, 3)
+        # the tables are 6-digit literals and NOT re-normalised (direction/mod.rs:58-75)
+        assert np.all(np.abs(np.linalg.norm(d.xyz, axis=1) - 1.0) < 2e-6)
+    assert Directions.from_num(1).xyz.tolist() == [[1.0, 0.0, 0.0]]
+    assert Directions.from_num(16).xyz[0].tolist() == [-0.887773, 0.0580969, -0.456601]
+    with pytest.raises(NotImplementedError):
+        Directions.from_num(17)
+    e = Directions.explicit([[2.0, 0.0, 0.0], [1.0, 1.0, 0.0]])
+    assert np.allclose(np.linalg.norm(e.xyz, axis=1), 1.0, atol=1e-15)
+
+
+@pytest.mark.parametrize("D", [1, 16, 21, 84])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_direction_shard_partitions(D, world):
+    lib = capi.load()
+    covered = []
+    for r in range(world):
+        b, e = direction_shard(D, world, r)
+        cb, ce = C.c_int32(), C.c_int32()
+        assert lib.ssw_direction_shard(D, world, r, C.byref(cb), C.byref(ce)) == 0
+        assert (cb.value, ce.value) == (b, e)
+        covered += list(range(b, e))
+    assert covered == list(range(D))
+    sizes = [direction_shard(D, world, r)[1] - direction_shard(D, world, r)[0] for r in range(world)]
+    assert max(sizes) - min(sizes) <= 1
+
+
+# src/sweep/timestep_level.rs:66-89 against the library's host-side rule
+@pytest.mark.parametrize("max_num_levels,secs_desired,result", [
+    (1, 1.0, 0), (2, 1.0, 0), (1, 0.001, 0), (2, 0.001, 1), (3, 0.001, 2), (2, 0.500001, 1),
+    (2, 0.499999, 1), (3, 0.499999, 2), (5, 100.0, 0), (5, 0.0, 4),
+])
+def test_library_level_rule(max_num_levels, secs_desired, result):
+    assert capi.load().ssw_level_from_timesteps(max_num_levels, 1.0, secs_desired) == result
+
+
+def test_library_level_rule_matches_oracle_on_random_input():
+    import oracle
+    lib, olib = capi.load(), oracle.load()
+    rng = np.random.default_rng(3)
+    vals = np.concatenate([10.0 ** rng.uniform(-30, 30, 20000), [0.0, np.inf, np.nan, -1.0, 1e-320],
+                           2.0 ** np.arange(-40, 40, dtype=np.float64)])
+    for L in (1, 2, 4, 7):
+        for v in vals:
+            assert lib.ssw_level_from_timesteps(L, 3.15576e13, float(v)) == olib.orc_level_from_timesteps(L, 3.15576e13, float(v))
+
+
+# src/sweep/timestep_state.rs:116-136
+def test_library_sweep_order():
+    lib = capi.load()
+
+    def order(L, lowest):
+        out = (C.c_int32 * 64)()
+        n = lib.ssw_levels_in_sweep_order(L, lowest, out, 64)
+        return list(out[:n])
+    assert order(5, 4) == [4]
+    assert order(5, 3) == [3, 4]
+    assert order(5, 2) == [2, 4, 3, 4]
+    assert order(5, 1) == [1, 4, 3, 4, 2, 4, 3, 4]
+    assert order(5, 0) == [0, 4, 3, 4, 2, 4, 3, 4, 1, 4, 3, 4, 2, 4, 3, 4]
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "subsweep_b200.h").read_text()
+    declared = set(re.findall(r"\b(ssw_[a-z_0-9]+)\s*\(", header))
+    declared -= {"ssw_allreduce_fn"}
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    lib = C.CDLL(str(capi.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert capi.load().ssw_abi_version() == 1
+
+
+def test_product_never_touches_the_oracle():
+    """No import, link, dlopen or call of anything under oracle/ from the product."""
+    pat = re.compile(r"(^|\s)(import|from)\s+oracle\b|liboracle|oracle\.h|\borc_[a-z]|oracle/")
+    files = list((ROOT / "subsweep_b200").rglob("*.py")) + list((ROOT / "subsweep_b200" / "csrc").glob("*.cu*"))
+    files += list((ROOT / "include").glob("*.h"))
+    assert files
+    for path in files:
+        m = pat.search(path.read_text())
+        assert m is None, (path, m.group(0))
+
+
+def test_create_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from helpers import make_problem
+    from subsweep_b200 import Sweep
+    params, g, f = make_problem(n=3, n_dirs=1)
+    with pytest.raises(capi.SubsweepError) as e:
+        Sweep(params, g, **f)
+    assert e.value.code == capi.SSW_E_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_units():
+    assert U.parse_quantity("1 Myr") == 1e6 * 3.15576e7
+    assert U.parse_quantity("2.5 kpc") == 2.5 * 1000 * 3.0857e16
+    assert U.parse_quantity(0.1) == 0.1
+    with pytest.raises(ValueError):
+        U.parse_quantity("1 parsecs")
