@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the sweep + chemistry hot path on B200 (driver contract).
+
+    python bench.py --gpus N --steps K --warmup W             # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU restatement on the host cores
+
+A *step* is one ``Sweep::run_sweeps`` call (src/sweep/mod.rs:258-272): every single sweep of the
+reference's level order, chemistry after each, and the timestep-level update.  The metric is
+BASELINE.json's: cell-direction updates per second, where one update is one solved task (cell,
+direction) and a step's updates are the sum over its single sweeps of (#active cells x D).
+
+Workload (``config.workload``): BASELINE.json configs[1] -- synthetic 128^3-cell periodic box,
+log-normal density, 64 point sources, 84 directions, 4 timestep levels (SURVEY.md section 8d,
+config 2, Cartesian variant; ``--grid voronoi`` tiles a periodic Voronoi block instead).
+For N > 1 the directions are sharded over the ranks (strong scaling: the total work is fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "cell_direction_updates_per_s"
+UNIT = "updates/s"
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+def build_workload(n: int, grid_kind: str, n_dirs: int, n_levels: int):
+    """SURVEY.md section 8d config 2 at n^3 cells (cell size fixed at 10 Mpc / 128)."""
+    from subsweep_b200 import SweepParameters, grid as G
+    from subsweep_b200 import units as U
+
+    cell = 10.0 * U.MEGAPARSEC / 128.0
+    box = cell * n
+    if grid_kind == "cartesian":
+        g = G.cartesian((n, n, n), box, periodic=True)
+    elif grid_kind == "voronoi":
+        unit_n = 16 if n % 16 == 0 else n
+        rng = np.random.default_rng(1338)
+        ijk = np.stack(np.meshgrid(*(np.arange(unit_n),) * 3, indexing="ij"), axis=-1).reshape(-1, 3)
+        pts = (ijk + 0.5 + 0.35 * rng.uniform(-1, 1, size=ijk.shape)) * cell
+        unit = G.voronoi(pts, cell * unit_n, periodic=True)
+        reps = n // unit_n
+        g = G.tile_periodic(unit, (reps, reps, reps)) if reps > 1 else unit
+    else:
+        raise ValueError(grid_kind)
+    N = g.n_cells
+    mean_rho = 1e-3 * U.PER_CUBIC_CENTIMETER * U.PROTON_MASS
+    rho = G.lognormal_density((n, n, n), mean_rho, sigma_g=1.0, smooth_cells=4.0, seed=2024)
+    if grid_kind == "voronoi":
+        # sample the field at the generator positions
+        idx = np.clip((g.positions / cell).astype(np.int64), 0, n - 1)
+        rho = rho.reshape(n, n, n)[idx[:, 0], idx[:, 1], idx[:, 2]]
+    n_src = max(1, int(round(64 * (n / 128.0) ** 3)))
+    src = np.zeros(N)
+    src[np.argsort(rho)[-n_src:]] = 1e52
+    fields = dict(density=np.ascontiguousarray(rho), ionized_hydrogen_fraction=np.full(N, 1e-10),
+                  temperature=np.full(N, 100.0), source=src)
+    params = SweepParameters(directions=n_dirs, num_timestep_levels=n_levels, periodic=True,
+                             max_timestep=1.0 * U.MEGAYEARS, significant_rate_threshold=1e-5,
+                             timestep_safety_factor=0.1, chemistry_timestep_safety_factor=0.1,
+                             prevent_cooling=True)
+    return params, g, fields
+
+
+def algorithmic_bytes_per_update(g, dirs) -> tuple[float, float]:
+    """B_alg = 20 * F_up + 24: per flux-carrying upwind face 8 B neighbour
+    flux + 4 B index + 8 B geometric share; per task 8 B source/periodic + 8 B attenuation input +
+    8 B outgoing flux write."""
+    sample = dirs[:: max(1, len(dirs) // 12)]
+    f_up = g.mean_upwind_faces(sample)
+    return 20.0 * f_up + 24.0, f_up
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.proc = None
+        self.lines: list[str] = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smax)) if smax else None,
+                "power_w_max": float(max(power)) if power else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arms (the oracle; the only place bench.py touches oracle/)
+# ---------------------------------------------------------------------------------------------
+def cpu_run(n: int, grid_kind: str, n_dirs: int, n_levels: int, steps: int, warmup: int, threads: int):
+    """The CPU restatement of the reference algorithm (oracle/, kind "port") on a bounded sample
+    of the workload: the same box at n^3 cells.  Returns (updates/s, ms per step, sample text)."""
+    import oracle
+    params, g, f = build_workload(n, grid_kind, n_dirs, n_levels)
+    s = oracle.OracleSweep(params, g, **f, periodic_mode=oracle.PERIODIC_LAGGED)
+    for _ in range(warmup):
+        s.run_sweeps_threads(threads)
+    t0_tasks = s.stat("tasks_solved")
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s.run_sweeps_threads(threads)
+    dt = time.perf_counter() - t0
+    tasks = s.stat("tasks_solved") - t0_tasks
+    sample = (f"{n}^3-cell box of the same workload (cell size, density field statistics, source density, "
+              f"{n_dirs} directions, {n_levels} levels), {warmup} warm-up + {steps} timed run_sweeps calls")
+    return tasks / dt, dt / steps * 1e3, sample, tasks
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    value, ms, sample, _ = cpu_run(args.cpu_n, args.grid, args.dirs, args.levels, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, note="CPU arm runs a bounded sample: " + sample),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, note: str | None = None) -> dict:
+    cfg = {
+        "workload": f"{args.n}^3-cell periodic box ({args.grid}), log-normal density, "
+                    f"{max(1, int(round(64 * (args.n / 128.0) ** 3)))} point sources of 1e52/s, {args.dirs} directions, "
+                    f"{args.levels} timestep levels, max_timestep 1 Myr (BASELINE.json configs[1])",
+        "cells": args.n ** 3, "directions": args.dirs, "timestep_levels": args.levels, "grid": args.grid,
+        "parallelism": f"direction sharding x{args.gpus}" if args.gpus > 1 else "single GPU",
+        "l2": "working set (per-direction flux state + level sets, > 2 GB) is far larger than the 126 MB L2; no flush needed",
+        "step": "one Sweep::run_sweeps call (all single sweeps of the level order + chemistry + level update)",
+    }
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def pinned(n: int) -> np.ndarray:
+    import torch
+    return torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
+
+
+def run_b200(args) -> None:
+    import torch
+    import torch.distributed as dist
+    from subsweep_b200 import Sweep, build as libbuild
+    from subsweep_b200.distributed import init_from_env, make_allreduce
+
+    rank, world, local_rank = init_from_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if rank == 0:
+        libbuild.build()
+    if world > 1:
+        dist.barrier()
+
+    params, g, fields = build_workload(args.n, args.grid, args.dirs, args.levels)
+    allreduce = make_allreduce(device) if world > 1 else None
+    sweep = Sweep(params, g, **fields, device_id=local_rank, rank=rank, world_size=world, allreduce=allreduce)
+    N = g.n_cells
+    b_alg, f_up = algorithmic_bytes_per_update(g, sweep.directions.xyz)
+
+    def sync_all():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(args.warmup):
+        sweep.run_sweeps()
+
+    # ---- timed region: K steps, inputs resident in HBM -------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    sweep.reset_timings()
+    tasks0, launches0 = sweep.stat("tasks_solved"), sweep.stat("kernel_launches")
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sweep.run_sweeps()
+    sync_all()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    tim = sweep.timings()
+    my_tasks = sweep.stat("tasks_solved") - tasks0
+    launches = sweep.stat("kernel_launches") - launches0
+    # device time of the K steps: CUDA events on the library's stream (ssw_timings.step_ms)
+    step_ms = torch.tensor([tim["step_ms"], wall * 1e3], dtype=torch.float64, device=device)
+    tot = torch.tensor([float(my_tasks), float(launches)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms, wall_ms = (float(v) for v in step_ms.tolist())
+    total_tasks, total_launches = (float(v) for v in tot.tolist())
+    value = total_tasks / (dev_ms * 1e-3)
+
+    # ---- end to end: host buffers in, host buffers out, every step --------------------------------
+    src_host = pinned(N)
+    src_host[:] = fields["source"]
+    outs = {k: pinned(N) for k in ("ionized_hydrogen_fraction", "temperature", "timestep", "photon_rate", "ionization_time")}
+    sync_all()
+    e_tasks0 = sweep.stat("tasks_solved")
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sweep.set_inputs(source=src_host)        # the Source component of this step (H2D)
+        sweep.run_sweeps()
+        for k, buf in outs.items():              # run_sweep_system write-back (D2H), mod.rs:718-738
+            sweep.read(k, buf)
+    sync_all()
+    e_wall = time.perf_counter() - t0
+    e = torch.tensor([e_wall], dtype=torch.float64, device=device)
+    et = torch.tensor([float(sweep.stat("tasks_solved") - e_tasks0)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        dist.all_reduce(et, op=dist.ReduceOp.SUM)
+    e2e_value = float(et.item()) / float(e.item())
+
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel: the all-cells sweep (current level 0) --------------------
+    peaks = {}
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peaks = json.loads(peaks_file.read_text())
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    lvl = int(np.argmax(tim["kernel_level_tasks"]))
+    k_ms = tim["kernel_level_ms"][lvl]
+    k_tasks = tim["kernel_level_tasks"][lvl]
+    k_launches = max(1, tim["kernel_level_launches"][lvl])
+    achieved = (b_alg * k_tasks / (k_ms * 1e-3)) / 1e9 if k_ms > 0 else 0.0
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "kernel": "sweep kernel of the all-cells single sweep (timestep level %d)" % lvl,
+        "algorithmic_bytes_per_update": b_alg, "mean_upwind_faces": f_up,
+        "updates_per_launch": k_tasks / k_launches, "ms_per_launch": k_ms / k_launches, "peak_source": peak_kind,
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        v, _, sample, _ = cpu_run(args.cpu_n, args.grid, args.dirs, args.levels, 2, args.warmup, threads)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N,
+                "d2h_bytes_per_step": 8 * N * len(outs)},
+        "gpu_launches": int(total_launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "timing": {"device_ms_total": dev_ms, "wall_ms_total": wall_ms, "updates_total": total_tasks,
+                   "sweep_ms": tim["sweep_ms"], "chemistry_ms": tim["chemistry_ms"],
+                   "update_levels_ms": tim["update_levels_ms"], "schedule_ms": tim["schedule_ms"],
+                   "allreduce_ms": tim["allreduce_ms"], "sweep_kernel_ms": tim["sweep_kernel_ms"],
+                   "sweep_level_ms": tim["sweep_level_ms"][:args.levels],
+                   "kernel_level_ms": tim["kernel_level_ms"][:args.levels],
+                   "kernel_level_tasks": tim["kernel_level_tasks"][:args.levels],
+                   "level_counts": [int(v) for v in sweep.level_counts()],
+                   "chem_attempts": sweep.stat("chem_attempts"), "chem_cells": sweep.stat("chem_cells"),
+                   "chem_max_depth": sweep.stat("chem_max_depth"), "wavefront_levels": sweep.stat("wavefront_levels"),
+                   "schedule_builds": sweep.stat("schedule_builds"), "schedule_replays": sweep.stat("schedule_replays")},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--n", type=int, default=128, help="cells per dimension")
+    ap.add_argument("--grid", choices=("cartesian", "voronoi"), default="cartesian")
+    ap.add_argument("--dirs", type=int, default=84)
+    ap.add_argument("--levels", type=int, default=4)
+    ap.add_argument("--cpu-n", type=int, default=48, help="cells per dimension of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3   # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

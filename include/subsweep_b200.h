@@ -182,6 +182,11 @@ typedef struct ssw_timings {
     uint64_t sweep_kernel_launches;
     uint64_t sweep_kernel_tasks;  /* cell-direction updates processed by those launches          */
     double sweep_level_ms[32];
+    double step_ms;           /* whole ssw_run_sweeps calls, first to last CUDA event on the stream */
+    uint64_t steps;
+    double kernel_level_ms[32];      /* sweep kernel time per current timestep level               */
+    uint64_t kernel_level_tasks[32]; /* cell-direction updates per current timestep level          */
+    uint64_t kernel_level_launches[32];
 } ssw_timings;
 int ssw_get_timings(ssw_handle *h, ssw_timings *out);
 int ssw_reset_timings(ssw_handle *h);

@@ -55,12 +55,16 @@ class Timings(C.Structure):
         ("sweep_ms", C.c_double), ("chemistry_ms", C.c_double), ("update_levels_ms", C.c_double),
         ("schedule_ms", C.c_double), ("allreduce_ms", C.c_double), ("sweep_kernel_ms", C.c_double),
         ("sweep_kernel_launches", C.c_uint64), ("sweep_kernel_tasks", C.c_uint64),
-        ("sweep_level_ms", C.c_double * 32),
+        ("sweep_level_ms", C.c_double * 32), ("step_ms", C.c_double), ("steps", C.c_uint64),
+        ("kernel_level_ms", C.c_double * 32), ("kernel_level_tasks", C.c_uint64 * 32),
+        ("kernel_level_launches", C.c_uint64 * 32),
     ]
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "sweep_level_ms"}
-        d["sweep_level_ms"] = list(self.sweep_level_ms)
+        d = {}
+        for k, t in self._fields_:
+            v = getattr(self, k)
+            d[k] = list(v) if hasattr(v, "__len__") else v
         return d
 
 

@@ -49,6 +49,35 @@ struct CellView {
     const int32_t *pidx;
 };
 
+// Flux state access.  Before the all-cells schedule is compiled the state is q = out / ttot in
+// the natural [dl][c] layout; afterwards it is out_slot (compiled.cuh) reached through slot_of.
+struct StateView {
+    double *q;
+    const uint32_t *slot_of;
+    double *out_slot;
+    const double *ttot_slot;
+    uint32_t n_cells;
+    __device__ __forceinline__ double load_q(uint32_t dl, uint32_t c) const {
+        const size_t t = (size_t)dl * n_cells + c;
+        if (slot_of) {
+            const uint32_t sl = __ldg(slot_of + t);
+            const double tt = __ldg(ttot_slot + sl);
+            return tt > 0.0 ? __ldcg(out_slot + sl) / tt : 0.0;
+        }
+        return __ldcg(q + t);
+    }
+    __device__ __forceinline__ double load_out(uint32_t dl, uint32_t c, double ttot) const {
+        const size_t t = (size_t)dl * n_cells + c;
+        if (slot_of) return __ldcg(out_slot + __ldg(slot_of + t));
+        return __ldcg(q + t) * ttot;
+    }
+    __device__ __forceinline__ void store(uint32_t dl, uint32_t c, double out, double ttot) const {
+        const size_t t = (size_t)dl * n_cells + c;
+        if (slot_of) __stcg(out_slot + __ldg(slot_of + t), out);
+        else __stcg(q + t, ttot > 0.0 ? out / ttot : 0.0);
+    }
+};
+
 // glam DVec3::dot without FMA contraction: the sign decides upwind / downwind
 // (src/sweep/grid/cell.rs:126-132) and must match the CPU bit for bit.
 __device__ __forceinline__ double dot_dir(const double4 &g, const double dx, const double dy,
@@ -121,7 +150,8 @@ struct SweepArgs {
     const double *src;      // per cell
     const int32_t *pidx;    // per cell
     const uint8_t *level;   // per cell
-    double *q;              // [dl][c]
+    StateView st;           // flux state
+    int solve;              // 0: only peel the level sets (no flux)
     double *incoming;       // [dl][c]
     const double *per_lag;  // [dl][p]
     int32_t *missing;       // [dl][c]
@@ -148,8 +178,7 @@ __device__ __forceinline__ void solve_task(const SweepArgs &a, uint32_t task, ui
         f0 = a.g.face_off[c];
         f1 = a.g.face_off[c + 1];
     }
-    if (valid && a.q != nullptr) {
-        const double *qd = a.q + (size_t)dl * N;
+    if (valid && a.solve) {
         double in = 0.0, ttot = 0.0;
         for (uint32_t f = f0; f < f1; ++f) {
             const double4 geo = ld_geo(a.g.face_geo + f);
@@ -157,7 +186,7 @@ __device__ __forceinline__ void solve_task(const SweepArgs &a, uint32_t task, ui
             if (d < 0.0) {
                 if (a.g.face_kind[f] == 0) {
                     const double w = __ldg(a.g.face_rev + f) * (-d);
-                    in += __ldcg(qd + a.g.face_nb[f]) * w;
+                    in += a.st.load_q(dl, (uint32_t)a.g.face_nb[f]) * w;
                 }
             } else if (d > 0.0) {
                 ttot += geo.w * d;
@@ -168,7 +197,7 @@ __device__ __forceinline__ void solve_task(const SweepArgs &a, uint32_t task, ui
         const double total = p >= 0 ? inc + a.per_lag[(size_t)dl * a.n_periodic + p] : inc + 0.0;
         // HydrogenOnly::get_outgoing_rate, hydrogen_only/mod.rs:81-87
         const double out = (total < a.threshold) ? 0.0 : total * a.att[c];
-        __stcg(a.q + (size_t)dl * N + c, ttot > 0.0 ? out / ttot : 0.0);
+        a.st.store(dl, c, out, ttot);
         __stcg(a.incoming + (size_t)dl * N + c, inc);
     }
     if (BUILD && valid && wlevel_dbg) wlevel_dbg[c] = wave;
@@ -266,18 +295,17 @@ sweep_replay_kernel(SweepArgs a, const uint32_t *__restrict__ queue,
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 periodic_gather_kernel(GridView g, const uint32_t *__restrict__ pcells, uint32_t n_periodic,
-                       const double *__restrict__ q, double *__restrict__ dst) {
+                       StateView st, double *__restrict__ dst) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const int dl = blockIdx.y;
     if (p >= n_periodic) return;
     const uint32_t c = pcells[p];
     const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
-    const double *qd = q + (size_t)dl * g.n_cells;
     double acc = 0.0;
     for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
         if (g.face_kind[f] != 2) continue;
         const double d = dot_dir(ld_geo(g.face_geo + f), dx, dy, dz);
-        if (d < 0.0) acc += qd[g.face_nb[f]] * (g.face_rev[f] * (-d));
+        if (d < 0.0) acc += st.load_q(dl, (uint32_t)g.face_nb[f]) * (g.face_rev[f] * (-d));
     }
     dst[(size_t)dl * n_periodic + p] = acc;
 }
@@ -285,14 +313,13 @@ periodic_gather_kernel(GridView g, const uint32_t *__restrict__ pcells, uint32_t
 // incoming_total_rate for every (cell, dir) from the current q (read-back / photon_rate,
 // src/sweep/mod.rs:727-730).  which: 0 incoming (Local faces), 2 periodic_source, 1 outgoing.
 __global__ void __launch_bounds__(256)
-dir_state_kernel(GridView g, const double *__restrict__ q, int which, int n_local_dirs,
+dir_state_kernel(GridView g, StateView st, int which, int n_local_dirs,
                  double *__restrict__ out_cell_major, double *__restrict__ photon_rate) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= g.n_cells) return;
     double total = 0.0;
     for (int dl = 0; dl < n_local_dirs; ++dl) {
         const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
-        const double *qd = q + (size_t)dl * g.n_cells;
         double acc = 0.0, ttot = 0.0;
         for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
             const double4 geo = ld_geo(g.face_geo + f);
@@ -300,12 +327,12 @@ dir_state_kernel(GridView g, const double *__restrict__ q, int which, int n_loca
             const int kind = g.face_kind[f];
             if (d < 0.0) {
                 if ((which == 0 && kind == 0) || (which == 2 && kind == 2))
-                    acc += qd[g.face_nb[f]] * (g.face_rev[f] * (-d));
+                    acc += st.load_q(dl, (uint32_t)g.face_nb[f]) * (g.face_rev[f] * (-d));
             } else if (d > 0.0) {
                 ttot += geo.w * d;
             }
         }
-        if (which == 1) acc = qd[c] * ttot;
+        if (which == 1) acc = st.load_out(dl, c, ttot);
         if (out_cell_major) out_cell_major[(size_t)c * n_local_dirs + dl] = acc;
         total += acc;
     }
@@ -439,19 +466,24 @@ __host__ __device__ inline int level_rule(int max_num_levels, double max_timeste
 __global__ void __launch_bounds__(256)
 levels_kernel(const double *__restrict__ tau, uint8_t *__restrict__ level, uint32_t n, int n_levels,
               double max_timestep, double safety, int lowest_allowed,
-              unsigned long long *__restrict__ hist /* 32 */) {
+              unsigned long long *__restrict__ hist /* 32 counts + [32] = number of changed cells */) {
     __shared__ unsigned int s_hist[32];
     if (threadIdx.x < 32) s_hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    bool changed = false;
     if (c < n) {
         int lv = level_rule(n_levels, max_timestep, safety * tau[c]);
         if (lv < lowest_allowed) lv = lowest_allowed;
-        level[c] = (uint8_t)lv;
+        if (level[c] != (uint8_t)lv) {
+            level[c] = (uint8_t)lv;
+            changed = true;
+        }
         atomicAdd(&s_hist[lv], 1u);
     }
-    __syncthreads();
+    const int any_changed = __syncthreads_or(changed ? 1 : 0);
     if (threadIdx.x < 32 && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
+    if (threadIdx.x == 0 && any_changed) atomicAdd(&hist[32], 1ull);
 }
 
 __global__ void __launch_bounds__(256)

@@ -96,7 +96,7 @@ struct Schedule {
     Compiled compiled;          // slot-ordered form (compiled.cuh), optional
 };
 
-enum TimerCat { T_SWEEP = 0, T_CHEM, T_LEVELS, T_SCHED, T_ALLREDUCE, T_KERNEL, T_COUNT };
+enum TimerCat { T_SWEEP = 0, T_CHEM, T_LEVELS, T_SCHED, T_ALLREDUCE, T_KERNEL, T_STEP, T_COUNT };
 
 struct Sweep {
     ssw_params P{};
@@ -145,6 +145,7 @@ struct Sweep {
     uint64_t levels_version = 1;
 
     std::vector<std::unique_ptr<Schedule>> sched;  // [0..L-1] partial sets by current level, [L] all cells
+    Compiled *state = nullptr;  // non-null once the flux state lives in slot order (compiled.cuh)
 
     ssw_allreduce_fn allreduce = nullptr;
     void *allreduce_ctx = nullptr;
@@ -202,7 +203,11 @@ struct Sweep {
                 case T_LEVELS: timings.update_levels_ms += ms; break;
                 case T_SCHED: timings.schedule_ms += ms; break;
                 case T_ALLREDUCE: timings.allreduce_ms += ms; break;
-                case T_KERNEL: timings.sweep_kernel_ms += ms; break;
+                case T_KERNEL:
+                    timings.sweep_kernel_ms += ms;
+                    if (p.lvl >= 0 && p.lvl < 32) timings.kernel_level_ms[p.lvl] += ms;
+                    break;
+                case T_STEP: timings.step_ms += ms; timings.steps += 1; break;
                 }
             }
             event_pool.push_back(p.a);
@@ -228,6 +233,15 @@ struct Sweep {
         c.size = size.p; c.volume = volume.p; c.level = level.p; c.pidx = pidx.p;
         return c;
     }
+    StateView state_view() const {
+        StateView st;
+        st.q = q.p;
+        st.slot_of = state ? state->slot_of : nullptr;
+        st.out_slot = state ? state->out_slot : nullptr;
+        st.ttot_slot = state ? state->ttot_slot : nullptr;
+        st.n_cells = N;
+        return st;
+    }
     SweepArgs sweep_args(int cur) const {
         SweepArgs a;
         a.g = grid_view();
@@ -235,7 +249,8 @@ struct Sweep {
         a.src = src.p;
         a.pidx = pidx.p;
         a.level = level.p;
-        a.q = q.p;
+        a.st = state_view();
+        a.solve = 1;
         a.incoming = incoming.p;
         a.per_lag = per_lag.p;
         a.missing = missing.p;
@@ -398,7 +413,7 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     rate_act.alloc(N);
     cell_tmp.alloc(N);
     cell_tmp2.alloc(N);
-    hist.alloc(32);
+    hist.alloc(33);
     chem_stats.alloc(1); chem_stats.zero(stream);
     CUDA_CHECK(cudaStreamSynchronize(stream));  // host vectors go out of scope
 
@@ -422,7 +437,7 @@ void Sweep::refresh_histogram() {
     hist.zero(stream);
     histogram_kernel<<<cdiv(N, 256), 256, 0, stream>>>(level.p, N, hist.p);
     launched();
-    unsigned long long h[32];
+    unsigned long long h[33];
     CUDA_CHECK(cudaMemcpyAsync(h, hist.p, sizeof h, cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
     for (int l = 0; l < P.n_levels; ++l) bin_count[l] = h[l];
@@ -449,7 +464,7 @@ void Sweep::build_active_list(Schedule &S, int cur) {
 void Sweep::gather_periodic(double *dst) {
     if (!n_periodic) return;
     dim3 grid(cdiv(n_periodic, 256), Dl);
-    periodic_gather_kernel<<<grid, 256, 0, stream>>>(grid_view(), pcells.p, n_periodic, q.p, dst);
+    periodic_gather_kernel<<<grid, 256, 0, stream>>>(grid_view(), pcells.p, n_periodic, state_view(), dst);
     launched();
 }
 
@@ -471,7 +486,7 @@ void Sweep::build_schedule(Schedule &S, int cur, bool solve, int dl_base, int n_
         CUDA_CHECK(cudaGetLastError());
     }
     SweepArgs a = sweep_args(cur);
-    if (!solve) { a.q = nullptr; a.incoming = nullptr; }
+    if (!solve) a.solve = 0;
     uint32_t *qp = queue_scratch.p;
     QueueCtl *cp = ctl.p;
     uint32_t *lo = level_off_scratch.p;
@@ -515,7 +530,8 @@ void Sweep::single_sweep(int cur) {
     const bool all = n_act == N;
     Schedule &S = *sched[all ? P.n_levels : cur];
     const bool cache_ok = !(P.flags & SSW_FLAG_NO_SCHEDULE_CACHE);
-    const bool reuse = cache_ok && S.valid && S.n_act == n_act && (all || S.version == levels_version);
+    const bool reuse = (all && S.compiled.valid) ||
+                       (cache_ok && S.valid && S.n_act == n_act && (all || S.version == levels_version));
     const size_t t_sweep = tic(T_SWEEP, cur);
 
     // periodic_source as the tasks of this sweep will read it (lagged)
@@ -524,14 +540,16 @@ void Sweep::single_sweep(int cur) {
     if (!reuse) {
         const size_t t_sched = tic(T_SCHED);
         S.valid = false;
-        S.compiled.release();
+        if (state != &S.compiled) S.compiled.release();
         S.n_act = n_act;
         if (!all) build_active_list(S, cur);
-        const size_t t_k = tic(T_KERNEL);
+        const size_t t_k = tic(T_KERNEL, cur);
         build_schedule(S, cur, /*solve=*/true, 0, Dl, nullptr);
         toc(t_k);
         timings.sweep_kernel_launches += 1;
         timings.sweep_kernel_tasks += S.n_tasks;
+        timings.kernel_level_tasks[cur] += S.n_tasks;
+        timings.kernel_level_launches[cur] += 1;
         // keep the level sets: sort every level by (direction, cell) so replays walk memory in order
         S.tasks.ensure(S.n_tasks);
         S.level_off.ensure(S.n_levels + 1);
@@ -553,17 +571,27 @@ void Sweep::single_sweep(int cur) {
         stat[SSW_STAT_SCHEDULE_BUILDS]++;
         toc(t_sched);
     } else {
-        const bool use_compiled = !(P.flags & SSW_FLAG_NO_COMPILED_PATH) && compiled_supported();
+        const bool use_compiled = all && !(P.flags & SSW_FLAG_NO_COMPILED_PATH) && compiled_supported();
         if (use_compiled && !S.compiled.valid) {
             const size_t t_sched = tic(T_SCHED);
-            compile_schedule(S.compiled, grid_view(), S.tasks.p, S.level_off_host, S.n_tasks, S.n_levels,
-                             Dl, pidx.p, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
+            try {
+                compile_schedule(S.compiled, grid_view(), S.tasks.p, S.level_off_host, S.n_tasks, S.n_levels,
+                                 Dl, q.p, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
+            } catch (const std::exception &e) {
+                fail(SSW_E_CUDA, "%s", e.what());
+            }
+            state = &S.compiled;   // out_slot is now the flux state; the natural-layout copy goes
+            q.release();
             toc(t_sched);
         }
-        const size_t t_k = tic(T_KERNEL);
+        const size_t t_k = tic(T_KERNEL, cur);
         SweepArgs a = sweep_args(cur);
         if (use_compiled && S.compiled.valid) {
-            run_compiled(S.compiled, a, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
+            try {
+                run_compiled(S.compiled, a, S.tasks.p, S.level_off.p, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
+            } catch (const std::exception &e) {
+                fail(SSW_E_CUDA, "%s", e.what());
+            }
         } else {
             const uint32_t *qp = S.tasks.p;
             const uint32_t *lo = S.level_off.p;
@@ -576,6 +604,8 @@ void Sweep::single_sweep(int cur) {
         toc(t_k);
         timings.sweep_kernel_launches += 1;
         timings.sweep_kernel_tasks += S.n_tasks;
+        timings.kernel_level_tasks[cur] += S.n_tasks;
+        timings.kernel_level_launches[cur] += 1;
         stat[SSW_STAT_SCHEDULE_REPLAYS]++;
     }
     stat[SSW_STAT_TASKS_SOLVED] += S.n_tasks;
@@ -610,17 +640,19 @@ void Sweep::update_timestep_levels() {
     levels_kernel<<<cdiv(N, 256), 256, 0, stream>>>(tau.p, level.p, N, P.n_levels, P.max_timestep_s,
                                                     P.timestep_safety_factor, lowest_allowed, hist.p);
     launched();
-    unsigned long long h[32];
+    unsigned long long h[33];
     CUDA_CHECK(cudaMemcpyAsync(h, hist.p, sizeof h, cudaMemcpyDeviceToHost, stream));
     toc(t);
     CUDA_CHECK(cudaStreamSynchronize(stream));
     for (int l = 0; l < P.n_levels; ++l) bin_count[l] = h[l];
-    levels_version++;
+    // level sets are rebuilt only when the active sets changed (north_star)
+    if (h[32] != 0) levels_version++;
 }
 
 // Sweep::run_sweeps (src/sweep/mod.rs:258-272)
 double Sweep::run_sweeps() {
     bind();
+    const size_t t_step = tic(T_STEP);
     std::vector<uint64_t> counts(P.n_levels);
     for (int l = 0; l < P.n_levels; ++l) counts[l] = count_at_least(l);   // :240-245
     std::vector<int32_t> order(1u << (P.n_levels - lowest_allowed - 1));
@@ -637,6 +669,7 @@ double Sweep::run_sweeps() {
     // fold the chemistry statistics
     ChemStats cs;
     CUDA_CHECK(cudaMemcpyAsync(&cs, chem_stats.p, sizeof cs, cudaMemcpyDeviceToHost, stream));
+    toc(t_step);
     resolve_timers();
     stat[SSW_STAT_CHEM_CELLS] = cs.cells;
     stat[SSW_STAT_CHEM_FAILURES] = cs.failures;
@@ -647,8 +680,8 @@ double Sweep::run_sweeps() {
 
 // sum_d get_rate(d) for every cell (Sweep::get_solver, src/sweep/mod.rs:616-620)
 void Sweep::all_rates(double *dev_out) {
-    dir_state_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), q.p, 0, Dl, nullptr, cell_tmp.p);
-    dir_state_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), q.p, 2, Dl, nullptr, cell_tmp2.p);
+    dir_state_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), state_view(), 0, Dl, nullptr, cell_tmp.p);
+    dir_state_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), state_view(), 2, Dl, nullptr, cell_tmp2.p);
     launched(2);
     const double frac = (double)Dl / (double)D;
     combine_rates_kernel<<<cdiv(N, 256), 256, 0, stream>>>(cell_tmp.p, cell_tmp2.p, src.p, frac, N, dev_out);
@@ -669,7 +702,7 @@ void Sweep::read_field(int field, double *out) {
     case SSW_F_SOURCE: srcp = src.p; break;
     case SSW_F_IONIZATION_TIME: srcp = ion_time.p; break;
     case SSW_F_PHOTON_RATE:
-        dir_state_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), q.p, 0, Dl, nullptr, cell_tmp.p);
+        dir_state_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), state_view(), 0, Dl, nullptr, cell_tmp.p);
         launched();
         maybe_allreduce(cell_tmp.p, N);
         srcp = cell_tmp.p;
@@ -863,7 +896,7 @@ int ssw_read_dir_state(ssw_handle *h, int32_t which, double *out) {
     s.bind();
     ssw::DevBuf<double> tmp;
     tmp.alloc((size_t)s.N * s.Dl);
-    ssw::dir_state_kernel<<<ssw::cdiv(s.N, 256), 256, 0, s.stream>>>(s.grid_view(), s.q.p, which, s.Dl, tmp.p, nullptr);
+    ssw::dir_state_kernel<<<ssw::cdiv(s.N, 256), 256, 0, s.stream>>>(s.grid_view(), s.state_view(), which, s.Dl, tmp.p, nullptr);
     s.launched();
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaMemcpyAsync(out, tmp.p, sizeof(double) * (size_t)s.N * s.Dl, cudaMemcpyDeviceToHost, s.stream));

@@ -4,7 +4,7 @@ level sets every time (SSW_FLAG_NO_SCHEDULE_CACHE)."""
 import numpy as np
 import pytest
 
-from helpers import make_problem
+from helpers import assert_close, make_problem
 from subsweep_b200 import Sweep, capi
 
 pytestmark = pytest.mark.gpu
@@ -26,9 +26,15 @@ def test_all_paths_bitwise_identical(cuda_lib, kind, n, periodic):
             assert s.stat("schedule_replays") > 0
         if name == "no_cache":
             assert s.stat("schedule_replays") == 0
-    for name in ("no_cache", "no_compiled"):
-        for k, v in results["default"].items():
-            assert np.array_equal(v, results[name][k], equal_nan=True), (name, k)
+    # fused build+solve and cached replay do the same arithmetic per task: bit-identical
+    for k, v in results["no_cache"].items():
+        assert np.array_equal(v, results["no_compiled"][k], equal_nan=True), k
+    # the compiled path folds 1 / sum_downwind(A n.d) into its precomputed shares: round-off only
+    for k, v in results["default"].items():
+        if k == "levels":
+            assert np.array_equal(v, results["no_compiled"][k])
+        else:
+            assert_close(v, results["no_compiled"][k], 1e-11, floor=1e-7 * np.nanmax(np.abs(v)), what=k)
 
 
 def test_sweep_plugin_surface(cuda_lib):
