@@ -19,7 +19,7 @@
 
 #include "../../include/subsweep_b200.h"
 #include "kernels.cuh"
-#include "compiled.cuh"
+#include "stream.cuh"
 
 namespace ssw {
 
@@ -132,7 +132,8 @@ struct Sweep {
     DevBuf<uint8_t> flags;
     DevBuf<uint8_t> cub_temp;
     DevBuf<uint32_t> n_selected;
-    DevBuf<double> rate_act, cell_tmp, cell_tmp2;
+    DevBuf<double> rate_act, cell_tmp, cell_tmp2, rate_cell;
+    DevBuf<double2> cellrec;
     DevBuf<unsigned long long> hist;
     DevBuf<ChemStats> chem_stats;
     DevBuf<int32_t> wlevel;
@@ -411,6 +412,8 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     flags.alloc(N);
     n_selected.alloc(1);
     rate_act.alloc(N);
+    rate_cell.alloc(N);
+    cellrec.alloc(N);
     cell_tmp.alloc(N);
     cell_tmp2.alloc(N);
     hist.alloc(33);
@@ -534,8 +537,10 @@ void Sweep::single_sweep(int cur) {
                        (cache_ok && S.valid && S.n_act == n_act && (all || S.version == levels_version));
     const size_t t_sweep = tic(T_SWEEP, cur);
 
-    // periodic_source as the tasks of this sweep will read it (lagged)
-    gather_periodic(per_lag.p);
+    const bool use_compiled = reuse && all && !(P.flags & SSW_FLAG_NO_COMPILED_PATH) && compiled_supported();
+    // periodic_source as the tasks of this sweep will read it (lagged); the
+    // compiled path reads the donors' previous outgoing rates directly (stream.cuh)
+    if (!use_compiled) gather_periodic(per_lag.p);
 
     if (!reuse) {
         const size_t t_sched = tic(T_SCHED);
@@ -571,12 +576,11 @@ void Sweep::single_sweep(int cur) {
         stat[SSW_STAT_SCHEDULE_BUILDS]++;
         toc(t_sched);
     } else {
-        const bool use_compiled = all && !(P.flags & SSW_FLAG_NO_COMPILED_PATH) && compiled_supported();
         if (use_compiled && !S.compiled.valid) {
             const size_t t_sched = tic(T_SCHED);
             try {
-                compile_schedule(S.compiled, grid_view(), S.tasks.p, S.level_off_host, S.n_tasks, S.n_levels,
-                                 Dl, q.p, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
+                compile_schedule(S.compiled, grid_view(), S.tasks.p, S.level_off.p, S.level_off_host, S.n_tasks,
+                                 S.n_levels, Dl, q.p, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
             } catch (const std::exception &e) {
                 fail(SSW_E_CUDA, "%s", e.what());
             }
@@ -588,7 +592,10 @@ void Sweep::single_sweep(int cur) {
         SweepArgs a = sweep_args(cur);
         if (use_compiled && S.compiled.valid) {
             try {
-                run_compiled(S.compiled, a, S.tasks.p, S.level_off.p, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
+                cellrec_kernel<<<cdiv(N, 256), 256, 0, stream>>>(att.p, src.p, (double)D, N, cellrec.p);
+                launched();
+                run_compiled(S.compiled, cellrec.p, rate_cell.p, N, P.significant_rate_threshold_per_s, /*solve=*/1,
+                             stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
             } catch (const std::exception &e) {
                 fail(SSW_E_CUDA, "%s", e.what());
             }
@@ -616,8 +623,11 @@ void Sweep::single_sweep(int cur) {
     const size_t t_chem = tic(T_CHEM);
     gather_periodic(per_new.p);
     const uint32_t *act = all ? nullptr : S.act_list.p;
-    rate_kernel<<<cdiv(n_act, 256), 256, 0, stream>>>(act, n_act, N, Dl, incoming.p, pidx.p, per_new.p,
-                                                      n_periodic, rate_act.p);
+    if (use_compiled && S.compiled.valid)
+        rate_finish_kernel<<<cdiv(N, 256), 256, 0, stream>>>(N, Dl, rate_cell.p, pidx.p, per_new.p, n_periodic, rate_act.p);
+    else
+        rate_kernel<<<cdiv(n_act, 256), 256, 0, stream>>>(act, n_act, N, Dl, incoming.p, pidx.p, per_new.p,
+                                                          n_periodic, rate_act.p);
     launched();
     maybe_allreduce(rate_act.p, n_act);
     ChemParams cp;
