@@ -279,7 +279,11 @@ def run_b200(args) -> None:
     # ---- end to end: host buffers in, host buffers out, every step --------------------------------
     if args.no_e2e:
         if rank == 0:
+            lvl0 = int(np.argmax(tim["kernel_level_tasks"]))
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": dev_ms / args.steps,
+                              "all_cells_sweep_ms": tim["kernel_level_ms"][lvl0] / max(1, tim["kernel_level_launches"][lvl0]),
+                              "sweep_ms": tim["sweep_ms"] / args.steps, "chemistry_ms": tim["chemistry_ms"] / args.steps,
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("SSW_")},
                               "note": "profiling run (--no-e2e): not a bench line"}), flush=True)
         return
     src_host = pinned(N)

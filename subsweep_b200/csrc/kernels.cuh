@@ -362,24 +362,6 @@ rate_kernel(const uint32_t *__restrict__ act_list, uint32_t n_act, uint32_t n_ce
     rate_act[k] = rate;
 }
 
-// the compiled path (stream.cuh) accumulates sum_d (incoming[d] + source / D) per cell during the
-// sweep; add the periodic_source terms of this sweep (site.rs:53-56)
-__global__ void __launch_bounds__(256)
-rate_finish_kernel(uint32_t n_cells, int n_local_dirs, const double *__restrict__ rate_cell,
-                   const int32_t *__restrict__ pidx, const double *__restrict__ per_new, uint32_t n_periodic,
-                   double *__restrict__ rate_act) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_cells) return;
-    double rate = rate_cell[c];
-    const int32_t p = pidx[c];
-    if (p >= 0) {
-        double per = 0.0;
-        for (int dl = 0; dl < n_local_dirs; ++dl) per += per_new[(size_t)dl * n_periodic + p];
-        rate += per;
-    }
-    rate_act[c] = rate;
-}
-
 // {exp(-n_HI sigma size), source / D} per cell: the 16-byte record the compiled sweep gathers
 __global__ void __launch_bounds__(256)
 cellrec_kernel(const double *__restrict__ att, const double *__restrict__ src, double n_dirs_total, uint32_t n,

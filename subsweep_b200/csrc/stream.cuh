@@ -5,15 +5,19 @@
 // one that dominates a step) has static level sets, so they are compiled once into a form the
 // hardware can stream:
 //
-//   * slot s = position of task (c, dl) in the level-sorted task list; inside a level the tasks
-//     are ordered by (cell, direction), so the directions of one cell that share a wavefront
-//     level are neighbours ("segment").
+//   * the local directions are dealt into G direction groups (dl % G).  A group is an
+//     independent wavefront pipeline with its own thread blocks (block b serves group b % G),
+//     level barriers and rate accumulators: while one group waits at a level barrier the
+//     co-resident blocks of the other groups keep the memory system busy.
+//   * slot s = position of task (c, dl) in the task list sorted by (wavefront level, group, cell,
+//     direction): the directions of one cell that share a (level, group) are neighbours
+//     ("segment").  A (level, group) pair is a "pseudo-level" pl = level * G + group.
 //   * the flux state lives in slot order: out_slot[s] = outgoing_total_rate of that task
-//     (src/sweep/site.rs:15); every level writes one contiguous range and gathers from ranges of
-//     earlier levels (the previous level's range is still in L2).
-//   * a level is cut into tiles of <= THREADS slots at segment boundaries.  Tile g is processed
-//     by block g % n_blocks; all static data of a tile -- per slot: cell index and entry
-//     offset, per upwind face ("entry"): source slot and the geometric share
+//     (src/sweep/site.rs:15); every pseudo-level writes one contiguous range and gathers from
+//     ranges of earlier levels (the previous level's range is still in L2).
+//   * a pseudo-level is cut into tiles of <= THREADS slots at segment boundaries.  The tiles of a
+//     group are dealt round-robin to the group's blocks; all static data of a tile -- per slot:
+//     cell index and entry offset, per upwind face ("entry"): source slot and the geometric share
 //     A_rev (-n.d) / sum_downwind(A n.d) of the donor (src/sweep/mod.rs:453-461) -- is packed
 //     into ONE contiguous packet, and the packets of a block are laid out back to back in the
 //     order the block consumes them.  A block therefore reads one sequential byte stream, which
@@ -24,23 +28,29 @@
 //     directly yields last sweep's value: the reference's lag (src/sweep/mod.rs:505-513,
 //     site.rs:53-56).  Donors in the same or an earlier level are
 //     redirected to a snapshot slot behind the task slots that is refreshed before each sweep.
-//   * per-cell photon rate: sum_d (incoming[d] + source / D) (src/sweep/mod.rs:554-558) is
-//     accumulated per segment through shared memory and added to rate_cell[c] by the one thread
-//     that owns the segment: no global atomics, deterministic order.  Different levels are
-//     ordered by the level barrier, and a cell has at most one segment per level.
-//   * level barrier: one counter per wavefront level, release-add by the blocks that own a tile
-//     of the level, acquire-poll by the first tile of the next level.
+//   * per-cell photon rate: sum_d incoming[d] (src/sweep/mod.rs:554-558) is reduced per segment
+//     with warp shuffles (+ one shared-memory hop across warps) and added to the group's
+//     accumulator acc_cell[g][c] by the one thread that owns the segment: no global atomics,
+//     deterministic order.  Levels are ordered by the level barrier, a cell has at most one
+//     segment per pseudo-level, and groups have separate accumulators.
+//   * the periodic_source terms of the rate (the donors' NEW outgoing rates, site.rs:53-56) are
+//     "epilogue" tiles: one extra pseudo-level per group behind its last wavefront level whose
+//     tasks are the (periodic cell, direction) pairs; they only accumulate into acc_per[g][p].
+//   * level barrier: one counter per pseudo-level, release-add by the blocks that own a tile of
+//     it, acquire-poll by the first tile of the dependent pseudo-level.
 //
-// Algorithmic bytes per cell-direction update as streamed from HBM: 12 B per entry (4 B slot +
-// 8 B share), 6 B per task of packet (cell 4 + entry offset 2), 8 B outgoing store; the 8 B
-// gathers per entry, the 16-B cell record and the rate accumulator are L2 traffic in the
-// steady state.  DESIGN.md section 5 compares this with B_alg = 20 F_up + 24.
+// Bytes per cell-direction update as streamed from HBM: 12 B per entry (4 B slot + 8 B share),
+// 6 B per task of packet (cell 4 + entry offset 2), 8 B outgoing store; the 8-B gathers per
+// entry, the 16-B cell record and the rate accumulators are L2 traffic in the steady state.
+// DESIGN.md section 5 compares this with B_alg = 20 F_up + 24.
 #pragma once
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -50,41 +60,64 @@
 namespace ssw {
 
 constexpr uint32_t kPeriodicBit = 0x80000000u;
-constexpr int kStreamThreads = 512;
+constexpr uint32_t kNoDep = 0xffffffffu;
+constexpr int kMaxStreamThreads = 512;
 constexpr int kMaxStages = 4;
+constexpr int kMaxGroups = 8;
+constexpr int kGroupShift = 40;   // sort key = group << 40 | (cell * Dl + dl)
 
 struct TileDesc {       // 16 B, one per tile, stored per block in consumption order
     uint32_t slot0;     // first slot of the tile
     uint32_t off16;     // packet offset inside the block's stream, in 16-B units
-    uint16_t n;         // slots in the tile (<= kStreamThreads)
+    uint16_t n;         // slots in the tile (<= THREADS)
     uint16_t n_entries; // upwind entries in the tile
-    uint32_t level;     // wavefront level
+    uint32_t level;     // pseudo-level
 };
 
+// first 32 bytes of a packet: what the consuming block needs to know about this tile and about
+// the tile it will prefetch into the same ring stage next (no global loads on the critical path)
+struct PacketHeader {
+    uint32_t slot0;
+    uint16_t n, n_entries;
+    uint32_t level;
+    uint32_t next_off16, next_bytes;   // packet of the tile `stages` positions later (bytes = 0: none)
+    uint32_t dep, dep_target;          // pseudo-level to wait for (kNoDep: none) and its arrival count
+    uint16_t scan_steps, pad;          // shuffle steps the longest segment of the tile needs
+};
+static_assert(sizeof(PacketHeader) == 32, "packet header is 32 bytes");
+
+// per-slot info word: entry offset in the tile | periodic entries << 16 | segment head << 31
+constexpr uint32_t kInfoHead = 0x80000000u;
+
 struct TileLayout {
-    uint32_t w, src, cell, eoff, bytes;
+    uint32_t w, src, cell, info, bytes;
 };
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
-// packet = [f64 share[E]] [u32 source slot[E]] [u32 cell[n]] [u16 entry offset[n + 1]], each padded to 16 B
+// packet = [header 32 B] [f64 share[E]] [u32 source slot[E]] [u32 cell[n]] [u32 info[n + 1]], each padded to 16 B.
+// The entries of a slot are its Local upwind faces in face order followed by its periodic ones.
 __host__ __device__ inline TileLayout tile_layout(uint32_t n, uint32_t E) {
     TileLayout L;
-    uint32_t o = 0;
+    uint32_t o = (uint32_t)sizeof(PacketHeader);
     L.w = o;    o += align16(8u * E);
     L.src = o;  o += align16(4u * E);
     L.cell = o; o += align16(4u * n);
-    L.eoff = o; o += align16(2u * (n + 1u));
+    L.info = o; o += align16(4u * (n + 1u));
     L.bytes = o;
     return L;
 }
 
 struct Compiled {
     bool valid = false;
-    uint64_t n_tasks = 0;
+    uint64_t n_tasks = 0;           // real tasks (slots with an outgoing rate)
+    uint64_t n_epilogue = 0;        // (periodic cell, direction) pairs
     uint64_t n_entries = 0;
-    uint32_t n_levels = 0;
+    uint32_t n_levels = 0;          // wavefront levels
+    uint32_t n_groups = 1;
+    uint32_t n_pl = 0;              // pseudo-levels: n_levels * G + G
     uint32_t n_tiles = 0;
     uint32_t n_lag = 0;             // snapshot slots behind the task slots
-    uint32_t n_blocks = 0, stages = 0, stage_bytes = 0;
+    uint32_t threads = 512, bps = 1, n_blocks = 0, stages = 0, stage_bytes = 0;
+    uint32_t n_cells = 0, n_periodic = 0;
     uint64_t stream_bytes = 0;
     double mean_entries = 0.0;
     uint32_t *slot_of = nullptr;    // [dl*N + c] -> slot
@@ -94,18 +127,22 @@ struct Compiled {
     unsigned char *stream = nullptr;
     TileDesc *tab = nullptr;        // n_tiles, block-major
     uint32_t *tab_off = nullptr;    // n_blocks + 1
-    uint64_t *stream_off = nullptr; // n_blocks
-    uint32_t *lvl_target = nullptr; // n_levels: blocks that own a tile of the level
-    unsigned int *lvl_count = nullptr; // n_levels arrival counters
+    uint64_t *stream_off = nullptr; // n_blocks + 1
+    uint32_t *lvl_target = nullptr; // n_pl: blocks that own a tile of the pseudo-level
+    uint32_t *lvl_dep = nullptr;    // n_pl: pseudo-level that must be complete first (kNoDep: none)
+    unsigned int *lvl_count = nullptr; // n_pl arrival counters
+    double *acc_cell = nullptr;     // G x N: sum_d incoming of the group's directions
+    double *acc_per = nullptr;      // G x n_periodic: sum_d periodic_source
     Compiled() = default;
     Compiled(const Compiled &) = delete;
     Compiled &operator=(const Compiled &) = delete;
     ~Compiled() { release(); }
     void release() {
         cudaFree(slot_of); cudaFree(out_slot); cudaFree(ttot_slot); cudaFree(lag_src); cudaFree(stream);
-        cudaFree(tab); cudaFree(tab_off); cudaFree(stream_off); cudaFree(lvl_target); cudaFree(lvl_count);
-        slot_of = lag_src = tab_off = lvl_target = nullptr;
-        out_slot = ttot_slot = nullptr;
+        cudaFree(tab); cudaFree(tab_off); cudaFree(stream_off); cudaFree(lvl_target); cudaFree(lvl_dep);
+        cudaFree(lvl_count); cudaFree(acc_cell); cudaFree(acc_per);
+        slot_of = lag_src = tab_off = lvl_target = lvl_dep = nullptr;
+        out_slot = ttot_slot = acc_cell = acc_per = nullptr;
         stream = nullptr;
         tab = nullptr;
         stream_off = nullptr;
@@ -118,15 +155,65 @@ inline bool compiled_supported() { return true; }
 
 // ---- construction kernels (run once per compiled schedule) -----------------------------------
 
-// task id (dl * N + c) -> cell-major sort key (c * Dl + dl)
+// task id (dl * N + c) -> sort key: group << 40 | (c * Dl + dl)
 __global__ void __launch_bounds__(256)
-s_key_kernel(const uint32_t *__restrict__ tasks, uint32_t n, uint32_t n_cells, uint32_t n_dl,
-             uint32_t *__restrict__ keys) {
+s_key64_kernel(const uint32_t *__restrict__ tasks, uint32_t n, uint32_t n_cells, uint32_t n_dl, uint32_t n_groups,
+               unsigned long long *__restrict__ keys) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const uint32_t t = tasks[s];
     const uint32_t dl = t / n_cells, c = t - dl * n_cells;
-    keys[s] = c * n_dl + dl;
+    keys[s] = ((unsigned long long)(dl % n_groups) << kGroupShift) | (unsigned long long)(c * n_dl + dl);
+}
+
+// epilogue candidates: i = p * Dl + dl; key = group << 40 | (c * Dl + dl) if the cell has a periodic
+// upwind face for dl, else ~0 (sorted to the end)
+__global__ void __launch_bounds__(256)
+s_epilogue_key_kernel(GridView g, const uint32_t *__restrict__ pcells, uint32_t n_periodic, uint32_t n_dl,
+                      uint32_t n_groups, unsigned long long *__restrict__ keys) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_periodic * n_dl) return;
+    const uint32_t p = i / n_dl, dl = i - p * n_dl;
+    const uint32_t c = pcells[p];
+    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    bool any = false;
+    for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f)
+        if (g.face_kind[f] == 2 && dot_dir(ld_geo(g.face_geo + f), dx, dy, dz) < 0.0) any = true;
+    keys[i] = any ? (((unsigned long long)(dl % n_groups) << kGroupShift) | (unsigned long long)(c * n_dl + dl))
+                  : ~0ull;
+}
+
+__device__ __forceinline__ uint32_t lower_bound_u64(const unsigned long long *__restrict__ a, uint32_t lo, uint32_t hi,
+                                                    unsigned long long v) {
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (a[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// pseudo-level offsets: pl_off[l * G + g] = first slot of (level l, group g); the epilogue
+// pseudo-levels [L * G + g] follow behind the n real tasks; pl_off[(L + 1) * G] = n + m
+__global__ void __launch_bounds__(256)
+s_pl_off_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ level_off, uint32_t n_levels,
+                uint32_t n_groups, const unsigned long long *__restrict__ epi_keys, uint32_t n_epi_cand, uint32_t n,
+                uint32_t *__restrict__ pl_off) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_real = n_levels * n_groups;
+    if (i < n_real) {
+        const uint32_t l = i / n_groups, g = i - l * n_groups;
+        pl_off[i] = lower_bound_u64(keys, level_off[l], level_off[l + 1], (unsigned long long)g << kGroupShift);
+    } else if (i <= n_real + n_groups) {
+        const uint32_t g = i - n_real;   // g == n_groups gives the end
+        pl_off[i] = n + lower_bound_u64(epi_keys, 0, n_epi_cand, (unsigned long long)g << kGroupShift);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+s_key32_kernel(const unsigned long long *__restrict__ keys64, uint32_t n, uint32_t *__restrict__ keys) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) keys[s] = (uint32_t)(keys64[s] & ((1ull << kGroupShift) - 1ull));
 }
 
 __global__ void __launch_bounds__(256)
@@ -139,29 +226,30 @@ s_slot_scatter_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t n_
     slot_of[(size_t)dl * n_cells + c] = s;
 }
 
-__device__ __forceinline__ uint32_t level_end_of_slot(const uint32_t *__restrict__ level_off, uint32_t n_levels,
-                                                      uint32_t s) {
-    // smallest level_off[l + 1] > s
-    uint32_t lo = 0, hi = n_levels;  // invariant: level_off[lo] <= s < level_off[hi]
+__device__ __forceinline__ uint32_t level_end_of_slot(const uint32_t *__restrict__ pl_off, uint32_t n_pl, uint32_t s) {
+    // smallest pl_off[l + 1] > s
+    uint32_t lo = 0, hi = n_pl;  // invariant: pl_off[lo] <= s < pl_off[hi]
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (level_off[mid] <= s) lo = mid;
+        if (pl_off[mid] <= s) lo = mid;
         else hi = mid;
     }
-    return level_off[hi];
+    return pl_off[hi];
 }
 
-// entries per slot (Local and LocalPeriodic upwind faces), total downwind effective area,
-// number of periodic entries whose donor is not in a later level (need a snapshot slot)
+// entries per slot, total downwind effective area, number of periodic entries whose donor is not
+// in a later level (they need a snapshot slot).  Real slots (s < n) count Local and LocalPeriodic
+// upwind faces, epilogue slots only the LocalPeriodic ones.
 __global__ void __launch_bounds__(256)
-s_count_kernel(GridView g, const uint32_t *__restrict__ keys, uint32_t n, uint32_t n_dl,
-               const uint32_t *__restrict__ slot_of, const uint32_t *__restrict__ level_off, uint32_t n_levels,
+s_count_kernel(GridView g, const uint32_t *__restrict__ keys, uint32_t n, uint32_t n_all, uint32_t n_dl,
+               const uint32_t *__restrict__ slot_of, const uint32_t *__restrict__ pl_off, uint32_t n_pl,
                uint32_t *__restrict__ cnt, double *__restrict__ ttot_slot, unsigned int *__restrict__ n_lag) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+    if (s >= n_all) return;
     const uint32_t k = keys[s];
     const uint32_t c = k / n_dl, dl = k - c * n_dl;
     const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    const bool real = s < n;
     uint32_t m = 0, lag = 0, lvl_end = 0;
     double ttot = 0.0;
     for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
@@ -169,37 +257,40 @@ s_count_kernel(GridView g, const uint32_t *__restrict__ keys, uint32_t n, uint32
         const double d = dot_dir(geo, dx, dy, dz);
         const int kind = g.face_kind[f];
         if (d < 0.0) {
-            if (kind == 0) ++m;
-            else if (kind == 2) {
+            if (kind == 0) {
+                if (real) ++m;
+            } else if (kind == 2) {
                 ++m;
-                if (lvl_end == 0) lvl_end = level_end_of_slot(level_off, n_levels, s);
-                if (slot_of[(size_t)dl * g.n_cells + (uint32_t)g.face_nb[f]] < lvl_end) ++lag;
+                if (real) {
+                    if (lvl_end == 0) lvl_end = level_end_of_slot(pl_off, n_pl, s);
+                    if (slot_of[(size_t)dl * g.n_cells + (uint32_t)g.face_nb[f]] < lvl_end) ++lag;
+                }
             }
         } else if (d > 0.0) {
             ttot += geo.w * d;
         }
     }
     cnt[s] = m;
-    ttot_slot[s] = ttot;
+    if (real) ttot_slot[s] = ttot;
     if (lag) atomicAdd(n_lag, lag);
 }
 
-// Greedy tile cutting, one warp per wavefront level: a tile is the longest run of <= max_slots
-// slots that ends at a segment (cell) boundary.  mode 0 counts, mode 1 writes the tile starts.
+// Greedy tile cutting, one warp per pseudo-level: a tile is the longest run of <= max_slots
+// slots that ends at a segment (cell) boundary.  Without tile_start only counts.
 __global__ void __launch_bounds__(128)
-s_cut_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ level_off, uint32_t n_levels,
-             uint32_t n_dl, uint32_t max_slots, const uint32_t *__restrict__ tile_off,
-             uint32_t *__restrict__ tile_cnt, uint32_t *__restrict__ tile_start) {
+s_cut_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pl_off, uint32_t n_pl, uint32_t n_dl,
+             uint32_t max_slots, const uint32_t *__restrict__ tile_off, uint32_t *__restrict__ tile_cnt,
+             uint32_t *__restrict__ tile_start) {
     const uint32_t l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    if (l >= n_levels) return;
-    const uint32_t begin = level_off[l], end = level_off[l + 1];
-    uint32_t start = begin, count = 0;
-    uint32_t out = tile_start ? tile_off[l] : 0;
+    if (l >= n_pl) return;
+    const uint32_t end = pl_off[l + 1];
+    uint32_t start = pl_off[l], count = 0;
+    const uint32_t out = tile_start ? tile_off[l] : 0;
     while (start < end) {
         if (tile_start && lane == 0) tile_start[out + count] = start;
         ++count;
-        uint32_t pos = start + max_slots;   // candidate end (exclusive)
+        const uint32_t pos = start + max_slots;   // candidate end (exclusive)
         if (pos >= end) break;
         // largest p in (start, pos] with cell(p) != cell(p - 1); segments are <= n_dl <= 128 long
         uint32_t best = 0;
@@ -226,31 +317,38 @@ struct FillArgs {
     GridView g;
     const uint32_t *keys;
     const uint32_t *slot_of;
-    const unsigned long long *upoff;   // n + 1
+    const int32_t *pidx;
+    const unsigned long long *upoff;   // n_all + 1
     const double *ttot_slot;
-    const uint32_t *level_off;
-    uint32_t n_levels, n_dl, n_tasks;
+    const uint32_t *pl_off;
+    uint32_t n_pl, n_real_pl, n_dl, n_tasks;
     const TileDesc *tab;          // block-major
     const uint32_t *tab_block;    // block of tile i (block-major index)
+    const uint32_t *tab_off;      // per block
+    const uint32_t *lvl_dep, *lvl_target;
     const uint64_t *stream_off;   // per block
     unsigned char *stream;
     uint32_t *lag_src;
     unsigned int *lag_counter;
+    uint32_t stages;
 };
 
 // one thread block per tile: writes the tile's packet
-__global__ void __launch_bounds__(kStreamThreads)
+__global__ void __launch_bounds__(kMaxStreamThreads)
 s_fill_kernel(FillArgs a) {
+    __shared__ uint32_t s_maxlen;
     const TileDesc d = a.tab[blockIdx.x];
     unsigned char *pkt = a.stream + a.stream_off[a.tab_block[blockIdx.x]] + (size_t)d.off16 * 16u;
     const TileLayout L = tile_layout(d.n, d.n_entries);
     double *w = reinterpret_cast<double *>(pkt + L.w);
     uint32_t *es = reinterpret_cast<uint32_t *>(pkt + L.src);
     uint32_t *cell = reinterpret_cast<uint32_t *>(pkt + L.cell);
-    uint16_t *eoff = reinterpret_cast<uint16_t *>(pkt + L.eoff);
+    uint32_t *info = reinterpret_cast<uint32_t *>(pkt + L.info);
     const unsigned long long e_base = a.upoff[d.slot0];
     const uint32_t tid = threadIdx.x;
-    if (tid == 0) eoff[d.n] = (uint16_t)d.n_entries;
+    const bool epilogue = d.level >= a.n_real_pl;
+    if (tid == 0) s_maxlen = 1;
+    __syncthreads();
     // zero the padding so the stream is fully initialised
     if (tid < 4) {
         if (tid == 0 && (d.n_entries & 1u)) w[d.n_entries] = 0.0;
@@ -258,40 +356,69 @@ s_fill_kernel(FillArgs a) {
         if (tid < pad_src) es[d.n_entries + tid] = 0u;
         const uint32_t pad_cell = (align16(4u * d.n) - 4u * d.n) / 4u;
         if (tid < pad_cell) cell[d.n + tid] = 0xffffffffu;
+        const uint32_t used = d.n + 1u, pad_info = (align16(4u * used) - 4u * used) / 4u;
+        if (tid < pad_info) info[used + tid] = 0u;
     }
-    if (tid < 8) {
-        const uint32_t used = d.n + 1u, pad = (align16(2u * used) - 2u * used) / 2u;
-        if (tid < pad) eoff[used + tid] = 0;
-    }
-    if (tid >= d.n) return;
-    const uint32_t s = d.slot0 + tid;
-    const uint32_t k = a.keys[s];
-    const uint32_t c = k / a.n_dl, dl = k - c * a.n_dl;
-    cell[tid] = c;
-    uint32_t e = (uint32_t)(a.upoff[s] - e_base);
-    eoff[tid] = (uint16_t)e;
-    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
-    uint32_t lvl_end = 0;
-    for (uint32_t f = a.g.face_off[c]; f < a.g.face_off[c + 1]; ++f) {
-        const int kind = a.g.face_kind[f];
-        if (kind != 0 && kind != 2) continue;
-        const double dd = dot_dir(ld_geo(a.g.face_geo + f), dx, dy, dz);
-        if (!(dd < 0.0)) continue;
-        uint32_t src = a.slot_of[(size_t)dl * a.g.n_cells + (uint32_t)a.g.face_nb[f]];
-        const double tt = a.ttot_slot[src];
-        const double share = tt > 0.0 ? (a.g.face_rev[f] * (-dd)) / tt : 0.0;
-        if (kind == 2) {
-            if (lvl_end == 0) lvl_end = level_end_of_slot(a.level_off, a.n_levels, s);
-            if (src < lvl_end) {   // donor not in a later level: read its pre-sweep snapshot
-                const unsigned int j = atomicAdd(a.lag_counter, 1u);
-                a.lag_src[j] = src;
-                src = a.n_tasks + j;
+    if (tid < d.n) {
+        const uint32_t s = d.slot0 + tid;
+        const uint32_t k = a.keys[s];
+        const uint32_t c = k / a.n_dl, dl = k - c * a.n_dl;
+        cell[tid] = epilogue ? (uint32_t)a.pidx[c] : c;   // epilogue tiles address acc_per by periodic row
+        const uint32_t e0 = (uint32_t)(a.upoff[s] - e_base);
+        uint32_t e = e0, n_per = 0;
+        const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+        uint32_t lvl_end = 0;
+        for (int pass = epilogue ? 1 : 0; pass < 2; ++pass) {   // Local faces first, then the periodic ones
+            for (uint32_t f = a.g.face_off[c]; f < a.g.face_off[c + 1]; ++f) {
+                if (a.g.face_kind[f] != (pass ? 2 : 0)) continue;
+                const double dd = dot_dir(ld_geo(a.g.face_geo + f), dx, dy, dz);
+                if (!(dd < 0.0)) continue;
+                uint32_t src = a.slot_of[(size_t)dl * a.g.n_cells + (uint32_t)a.g.face_nb[f]];
+                const double tt = a.ttot_slot[src];
+                const double share = tt > 0.0 ? (a.g.face_rev[f] * (-dd)) / tt : 0.0;
+                if (pass) {
+                    ++n_per;
+                    if (!epilogue) {
+                        if (lvl_end == 0) lvl_end = level_end_of_slot(a.pl_off, a.n_pl, s);
+                        if (src < lvl_end) {   // donor not in a later level: read its pre-sweep snapshot
+                            const unsigned int j = atomicAdd(a.lag_counter, 1u);
+                            a.lag_src[j] = src;
+                            src = a.n_tasks + j;
+                        }
+                    }
+                }
+                es[e] = src;
+                w[e] = share;
+                ++e;
             }
-            src |= kPeriodicBit;
         }
-        es[e] = src;
-        w[e] = share;
-        ++e;
+        if (n_per > 255u) atomicAdd(a.lag_counter + 1, 1u);   // reported as an error by the host
+        const bool head = tid == 0 || a.keys[s - 1] / a.n_dl != c;
+        info[tid] = e0 | (min(n_per, 255u) << 16) | (head ? kInfoHead : 0u);
+        if (head) {   // segment length -> shuffle steps
+            uint32_t len = 1;
+            while (tid + len < d.n && a.keys[s + len] / a.n_dl == c) ++len;
+            atomicMax(&s_maxlen, len);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        info[d.n] = d.n_entries;
+        PacketHeader h;
+        h.slot0 = d.slot0; h.n = d.n; h.n_entries = d.n_entries; h.level = d.level;
+        h.next_off16 = 0; h.next_bytes = 0; h.pad = 0;
+        h.dep = a.lvl_dep[d.level];
+        h.dep_target = h.dep != kNoDep ? a.lvl_target[h.dep] : 0u;
+        uint32_t steps = 0;
+        while ((1u << steps) < min(s_maxlen, 32u)) ++steps;
+        h.scan_steps = (uint16_t)steps;
+        const uint32_t nxt = blockIdx.x + a.stages;
+        if (nxt < a.tab_off[a.tab_block[blockIdx.x] + 1]) {
+            const TileDesc nd = a.tab[nxt];
+            h.next_off16 = nd.off16;
+            h.next_bytes = tile_layout(nd.n, nd.n_entries).bytes;
+        }
+        *reinterpret_cast<PacketHeader *>(pkt) = h;
     }
 }
 
@@ -311,6 +438,29 @@ s_lag_snapshot_kernel(const uint32_t *__restrict__ lag_src, uint32_t n_lag, uint
                       double *__restrict__ out_slot) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n_lag) out_slot[n_tasks + j] = out_slot[lag_src[j]];
+}
+
+// rate_act[c] = sum_d ((incoming[d] + source / D) + periodic_source[d]) over this rank's directions
+// (src/sweep/mod.rs:554-558, site.rs:53-56) from the group accumulators of the compiled sweep
+__global__ void __launch_bounds__(256)
+s_rate_finish_kernel(uint32_t n_cells, uint32_t n_groups, uint32_t n_periodic, int n_local_dirs, double n_dirs_total,
+                     const double *__restrict__ acc_cell, const double *__restrict__ acc_per,
+                     const int32_t *__restrict__ pidx, const double *__restrict__ src, double *__restrict__ rate_act,
+                     double *__restrict__ photon) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    double in = 0.0;
+    for (uint32_t g = 0; g < n_groups; ++g) in += acc_cell[(size_t)g * n_cells + c];
+    if (photon) photon[c] = in;                              // photon_rate, mod.rs:727-730
+    if (!rate_act) return;
+    double rate = in;
+    const int32_t p = pidx[c];
+    if (p >= 0) {
+        double per = 0.0;
+        for (uint32_t g = 0; g < n_groups; ++g) per += acc_per[(size_t)g * n_periodic + p];
+        rate += per;
+    }
+    rate_act[c] = rate + (src[c] / n_dirs_total) * (double)n_local_dirs;
 }
 
 // ---- PTX helpers: mbarrier + TMA bulk copy ------------------------------------------------------
@@ -341,11 +491,12 @@ __device__ __forceinline__ void tma_bulk_load(uint32_t dst, const void *src, uin
 __device__ __forceinline__ void red_release_gpu(unsigned int *p) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p) {
     unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 struct StreamArgs {
     const unsigned char *stream;
@@ -353,143 +504,214 @@ struct StreamArgs {
     const TileDesc *tab;
     const uint32_t *tab_off;
     const uint32_t *lvl_target;
+    const uint32_t *lvl_dep;
     unsigned int *lvl_count;
     double *out_slot;
     const double2 *cellrec;   // {exp(-n_HI sigma size), source / D} per cell
-    double *rate_cell;        // per cell sum over this rank's directions of incoming + source / D
+    double *acc_cell;         // G x N
+    double *acc_per;          // G x n_periodic
     double threshold;
     uint32_t stages, stage_bytes;
+    uint32_t n_groups, n_real_pl, n_cells, n_periodic;
     int solve;                // 1: sweep; 0: only accumulate sum_d incoming (photon_rate read-out)
+    unsigned long long *prof; // optional per-block cycle counters {total, level barrier, packet wait, tiles}
 };
 
-// Persistent kernel: block b consumes the tiles tab[tab_off[b] .. tab_off[b+1]) in order.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Persistent kernel: block b consumes the tiles tab[tab_off[b] .. tab_off[b+1]) in order.  Per tile:
+//   phase 1 (entry-parallel)  prod[e] = out_slot[source slot[e]] * share[e], written over share[e] in the
+//                             ring stage: every gather of the tile is independent and in flight at once
+//   phase 2 (task-parallel)   a thread sums the products of its slot (Local faces in face order, then
+//                             the periodic ones), applies the absorption and stores the outgoing rate;
+//                             the per-cell rate is reduced over the segment with warp shuffles
+template <int THREADS, int MIN_BLOCKS, bool PROFILE>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 sweep_stream_kernel(StreamArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *ring = smem;
-    double *inc_s = reinterpret_cast<double *>(smem + (size_t)a.stages * a.stage_bytes);
-    uint64_t *full = reinterpret_cast<uint64_t *>(inc_s + THREADS);
-    const uint32_t tid = threadIdx.x;
-    const uint32_t t0 = a.tab_off[blockIdx.x], n_my = a.tab_off[blockIdx.x + 1] - t0;
-    const TileDesc *tab = a.tab + t0;
-    const unsigned char *stream = a.stream + a.stream_off[blockIdx.x];
+    constexpr int WARPS = THREADS / 32;
+    __shared__ double s_wsum[2][WARPS];
+    __shared__ uint32_t s_wfirst[2][WARPS], s_wlast[2][WARPS];
+    unsigned char *const ring = smem;
+    const uint32_t stages = a.stages, stage_bytes = a.stage_bytes;
+    uint64_t *const full = reinterpret_cast<uint64_t *>(smem + (size_t)stages * stage_bytes);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n_my = a.tab_off[blockIdx.x + 1] - a.tab_off[blockIdx.x];
+    const unsigned char *const stream = a.stream + a.stream_off[blockIdx.x];
+    const uint32_t grp = blockIdx.x % a.n_groups;
+    double *const acc_cell = a.acc_cell + (size_t)grp * a.n_cells;
+    double *const acc_per = a.acc_per + (size_t)grp * a.n_periodic;
+    double *const out_slot = a.out_slot;
+    const uint32_t n_real_pl = a.n_real_pl;
+    const int solve = a.solve;
+    const double threshold = a.threshold;
     uint64_t policy = 0;
     if (tid == 0) {
-        for (uint32_t s = 0; s < a.stages; ++s) mbar_init(smem_u32(full + s), 1);
+        for (uint32_t s = 0; s < stages; ++s) mbar_init(smem_u32(full + s), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         policy = policy_evict_first();
     }
     __syncthreads();
     if (tid == 0) {
-        const uint32_t pre = min(a.stages, n_my);
+        const TileDesc *tab = a.tab + a.tab_off[blockIdx.x];
+        const uint32_t pre = min(stages, n_my);
         for (uint32_t k = 0; k < pre; ++k) {
             const TileDesc d = tab[k];
             const uint32_t bytes = tile_layout(d.n, d.n_entries).bytes;
             mbar_expect_tx(smem_u32(full + k), bytes);
-            tma_bulk_load(smem_u32(ring + (size_t)k * a.stage_bytes), stream + (size_t)d.off16 * 16u, bytes,
+            tma_bulk_load(smem_u32(ring + (size_t)k * stage_bytes), stream + (size_t)d.off16 * 16u, bytes,
                           smem_u32(full + k), policy);
         }
     }
-    uint32_t prev_level = 0xffffffffu;
+    uint32_t prev_level = kNoDep;
     uint32_t stage = 0, parity = 0;
+    long long t_begin = 0, t_bar = 0, t_pkt = 0, tp = 0;
+    if (PROFILE && tid == 0) t_begin = clock64();
     for (uint32_t k = 0; k < n_my; ++k) {
-        const TileDesc d = tab[k];
+        if (PROFILE && tid == 0) tp = clock64();
+        mbar_wait(smem_u32(full + stage), parity);
+        if (PROFILE && tid == 0) t_pkt += clock64() - tp;
+        unsigned char *const pkt = ring + (size_t)stage * stage_bytes;
+        const PacketHeader d = *reinterpret_cast<const PacketHeader *>(pkt);
         if (d.level != prev_level) {
-            // all stores of the previous level were issued before the tile-end barrier below
+            __syncthreads();   // every thread has issued all its stores of the previous pseudo-level
             if (tid == 0) {
-                if (prev_level != 0xffffffffu) red_release_gpu(a.lvl_count + prev_level);
-                if (d.level > 0) {
-                    const unsigned int target = a.lvl_target[d.level - 1];
-                    while (ld_acquire_gpu(a.lvl_count + d.level - 1) < target) {}
+                if (PROFILE) tp = clock64();
+                if (prev_level != kNoDep) red_release_gpu(a.lvl_count + prev_level);
+                if (d.dep != kNoDep) {
+                    while (ld_relaxed_gpu(a.lvl_count + d.dep) < d.dep_target) {}
+                    fence_acq_rel_gpu();
                 }
+                if (PROFILE) t_bar += clock64() - tp;
             }
             __syncthreads();
             prev_level = d.level;
         }
-        mbar_wait(smem_u32(full + stage), parity);
-        const unsigned char *pkt = ring + (size_t)stage * a.stage_bytes;
-        const TileLayout L = tile_layout(d.n, d.n_entries);
-        const double *w = reinterpret_cast<const double *>(pkt + L.w);
-        const uint32_t *es = reinterpret_cast<const uint32_t *>(pkt + L.src);
-        const uint32_t *cell = reinterpret_cast<const uint32_t *>(pkt + L.cell);
-        const uint16_t *eoff = reinterpret_cast<const uint16_t *>(pkt + L.eoff);
-        uint32_t c = 0xffffffffu;
-        double inc = 0.0;
-        if (tid < d.n) {
+        const bool epilogue = d.level >= n_real_pl;
+        double *const acc = epilogue ? acc_per : acc_cell;
+        const uint32_t n = d.n, E = d.n_entries;
+        const TileLayout L = tile_layout(n, E);
+        double *const prod = reinterpret_cast<double *>(pkt + L.w);
+        const uint32_t *const es = reinterpret_cast<const uint32_t *>(pkt + L.src);
+        const uint32_t *const cell = reinterpret_cast<const uint32_t *>(pkt + L.cell);
+        const uint32_t *const info = reinterpret_cast<const uint32_t *>(pkt + L.info);
+
+        // per-slot data whose latency hides behind phase 1
+        uint32_t c = 0xffffffffu, inf = 0, e1 = 0;
+        double acc_old = 0.0;
+        double2 rec = make_double2(0.0, 0.0);
+        if (tid < n) {
             c = cell[tid];
-            uint32_t e = eoff[tid];
-            const uint32_t e1 = eoff[tid + 1];
-            const double2 rec = __ldg(a.cellrec + c);
-            double in_loc = 0.0, in_per = 0.0;
-            // gathers of four entries are issued together (memory-level parallelism), the sums
-            // run in face order like the reference's accumulation
-            for (; e + 4 <= e1; e += 4) {
-                const uint32_t s0 = es[e], s1 = es[e + 1], s2 = es[e + 2], s3 = es[e + 3];
-                const double v0 = __ldcg(a.out_slot + (s0 & ~kPeriodicBit));
-                const double v1 = __ldcg(a.out_slot + (s1 & ~kPeriodicBit));
-                const double v2 = __ldcg(a.out_slot + (s2 & ~kPeriodicBit));
-                const double v3 = __ldcg(a.out_slot + (s3 & ~kPeriodicBit));
-                const double p0 = v0 * w[e], p1 = v1 * w[e + 1], p2 = v2 * w[e + 2], p3 = v3 * w[e + 3];
-                if (s0 & kPeriodicBit) in_per += p0; else in_loc += p0;
-                if (s1 & kPeriodicBit) in_per += p1; else in_loc += p1;
-                if (s2 & kPeriodicBit) in_per += p2; else in_loc += p2;
-                if (s3 & kPeriodicBit) in_per += p3; else in_loc += p3;
-            }
-            {
-                const uint32_t r = e1 - e;   // 0..3 remaining
-                const uint32_t s0 = r > 0 ? es[e] : 0u, s1 = r > 1 ? es[e + 1] : 0u, s2 = r > 2 ? es[e + 2] : 0u;
-                const double v0 = r > 0 ? __ldcg(a.out_slot + (s0 & ~kPeriodicBit)) : 0.0;
-                const double v1 = r > 1 ? __ldcg(a.out_slot + (s1 & ~kPeriodicBit)) : 0.0;
-                const double v2 = r > 2 ? __ldcg(a.out_slot + (s2 & ~kPeriodicBit)) : 0.0;
-                if (r > 0) { const double p = v0 * w[e]; if (s0 & kPeriodicBit) in_per += p; else in_loc += p; }
-                if (r > 1) { const double p = v1 * w[e + 1]; if (s1 & kPeriodicBit) in_per += p; else in_loc += p; }
-                if (r > 2) { const double p = v2 * w[e + 2]; if (s2 & kPeriodicBit) in_per += p; else in_loc += p; }
-            }
-            if (a.solve) {
-                inc = in_loc + rec.y;                                   // site.rs:49-56
-                const double total = inc + in_per;
-                // HydrogenOnly::get_outgoing_rate, hydrogen_only/mod.rs:81-87
-                const double out = (total < a.threshold) ? 0.0 : total * rec.x;
-                __stcg(a.out_slot + d.slot0 + tid, out);
-            } else {
-                inc = in_loc;                                           // photon_rate, mod.rs:727-730
-            }
+            inf = info[tid];
+            e1 = info[tid + 1] & 0xffffu;
+            if (inf & kInfoHead) acc_old = __ldcg(acc + c);
+            if (!epilogue) rec = __ldg(a.cellrec + c);
         }
-        inc_s[tid] = inc;
+        // phase 1: four independent gathers per thread and round
+        for (uint32_t i = tid; i < E; i += 4u * THREADS) {
+            const uint32_t i1 = i + THREADS, i2 = i + 2u * THREADS, i3 = i + 3u * THREADS;
+            const bool p1 = i1 < E, p2 = i2 < E, p3 = i3 < E;
+            double v0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+            v0 = __ldcg(out_slot + (es[i] & ~kPeriodicBit));
+            if (p1) v1 = __ldcg(out_slot + (es[i1] & ~kPeriodicBit));
+            if (p2) v2 = __ldcg(out_slot + (es[i2] & ~kPeriodicBit));
+            if (p3) v3 = __ldcg(out_slot + (es[i3] & ~kPeriodicBit));
+            prod[i] = v0 * prod[i];
+            if (p1) prod[i1] = v1 * prod[i1];
+            if (p2) prod[i2] = v2 * prod[i2];
+            if (p3) prod[i3] = v3 * prod[i3];
+        }
         __syncthreads();
-        // segment heads fold their segment in direction order and own the cell's accumulator
-        if (tid < d.n && (tid == 0 || cell[tid - 1] != c)) {
-            double sum = inc;
-            for (uint32_t j = tid + 1; j < d.n && cell[j] == c; ++j) sum += inc_s[j];
-            __stcg(a.rate_cell + c, __ldcg(a.rate_cell + c) + sum);
+        // phase 2
+        double inc = 0.0;
+        if (tid < n) {
+            uint32_t e = inf & 0xffffu;
+            const uint32_t em = e1 - ((inf >> 16) & 0xffu);
+            double in_loc = 0.0, in_per = 0.0;
+            for (; e < em; ++e) in_loc += prod[e];
+            for (; e < e1; ++e) in_per += prod[e];
+            if (epilogue) {
+                inc = solve ? in_per : 0.0;                             // periodic_source of this sweep
+            } else {
+                inc = in_loc;                                           // incoming_total_rate[d]
+                if (solve) {
+                    const double total = (in_loc + rec.y) + in_per;     // site.rs:49-56
+                    // HydrogenOnly::get_outgoing_rate, hydrogen_only/mod.rs:81-87
+                    const double out = (total < threshold) ? 0.0 : total * rec.x;
+                    __stcg(out_slot + d.slot0 + tid, out);
+                }
+            }
         }
-        __syncthreads();   // the stage and inc_s are free again
-        if (tid == 0 && k + a.stages < n_my) {
-            const TileDesc nd = tab[k + a.stages];
-            const uint32_t bytes = tile_layout(nd.n, nd.n_entries).bytes;
-            mbar_expect_tx(smem_u32(full + stage), bytes);
-            tma_bulk_load(smem_u32(ring + (size_t)stage * a.stage_bytes), stream + (size_t)nd.off16 * 16u, bytes,
-                          smem_u32(full + stage), policy);
+        // segmented suffix sums over the lanes of a warp: a lane ends up with the sum of its segment
+        // from itself to the segment's end inside the warp
+        double sum = inc;
+        for (uint32_t st = 0, o = 1; st < d.scan_steps; ++st, o <<= 1) {
+            const double v = __shfl_down_sync(0xffffffffu, sum, o);
+            const uint32_t cc = __shfl_down_sync(0xffffffffu, c, o);
+            if (lane + o < 32u && cc == c) sum += v;
         }
-        if (++stage == a.stages) { stage = 0; parity ^= 1u; }
+        const uint32_t c_last = __shfl_sync(0xffffffffu, c, 31);
+        const uint32_t buf = k & 1u;
+        if (lane == 0) {
+            s_wsum[buf][warp] = sum;
+            s_wfirst[buf][warp] = c;
+            s_wlast[buf][warp] = c_last;
+        }
+        __syncthreads();   // all threads are done with the stage; warp partial sums are visible
+        if (tid == 0 && d.next_bytes) {
+            fence_proxy_async_smem();   // the products were written through the generic proxy
+            mbar_expect_tx(smem_u32(full + stage), d.next_bytes);
+            tma_bulk_load(smem_u32(pkt), stream + (size_t)d.next_off16 * 16u, d.next_bytes, smem_u32(full + stage),
+                          policy);
+        }
+        if (inf & kInfoHead) {
+            if (c_last == c) {   // the segment runs on into the following warps
+                for (uint32_t ww = warp + 1; ww < (uint32_t)WARPS && s_wfirst[buf][ww] == c; ++ww) {
+                    sum += s_wsum[buf][ww];
+                    if (s_wlast[buf][ww] != c) break;
+                }
+            }
+            if (solve || !epilogue) __stcg(acc + c, acc_old + sum);
+        }
+        if (++stage == stages) { stage = 0; parity ^= 1u; }
     }
-    // the last level of this block: nobody waits for the final level, but keep the counters
-    // complete so that a later launch (after the memset) and debugging see a consistent state
-    if (tid == 0 && prev_level != 0xffffffffu) red_release_gpu(a.lvl_count + prev_level);
+    __syncthreads();
+    if (tid == 0 && prev_level != kNoDep) red_release_gpu(a.lvl_count + prev_level);
+    if (PROFILE && tid == 0) {
+        a.prof[4 * blockIdx.x + 0] = (unsigned long long)(clock64() - t_begin);
+        a.prof[4 * blockIdx.x + 1] = (unsigned long long)t_bar;
+        a.prof[4 * blockIdx.x + 2] = (unsigned long long)t_pkt;
+        a.prof[4 * blockIdx.x + 3] = n_my;
+    }
 }
 
 // ---- host side --------------------------------------------------------------------------------------
-struct StreamLaunchConfig {
-    uint32_t blocks_per_sm, stages, stage_bytes, smem_bytes;
-};
+typedef void (*StreamKernel)(StreamArgs);
+
+inline StreamKernel stream_kernel_for(uint32_t threads, uint32_t blocks_per_sm, bool profile = false) {
+    if (profile) return threads == 256 ? sweep_stream_kernel<256, 4, true> : sweep_stream_kernel<512, 2, true>;
+    if (threads == 256) {
+        if (blocks_per_sm >= 8) return sweep_stream_kernel<256, 8, false>;
+        if (blocks_per_sm >= 6) return sweep_stream_kernel<256, 6, false>;
+        return sweep_stream_kernel<256, 4, false>;
+    }
+    if (blocks_per_sm >= 4) return sweep_stream_kernel<512, 4, false>;
+    if (blocks_per_sm >= 3) return sweep_stream_kernel<512, 3, false>;
+    return sweep_stream_kernel<512, 2, false>;
+}
 
 inline size_t stream_smem_bytes(uint32_t stages, uint32_t stage_bytes) {
-    return (size_t)stages * stage_bytes + sizeof(double) * kStreamThreads + sizeof(uint64_t) * kMaxStages;
+    return (size_t)stages * stage_bytes + sizeof(uint64_t) * kMaxStages;
 }
 
 inline void cuda_ok(cudaError_t e, const char *what) {
     if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+inline uint32_t env_u32(const char *name, uint32_t fallback) {
+    const char *v = std::getenv(name);
+    if (!v || !*v) return fallback;
+    return (uint32_t)std::strtoul(v, nullptr, 10);
 }
 
 // Builds the compiled schedule from the level-sorted task list of the all-cells sweep.
@@ -497,56 +719,96 @@ inline void cuda_ok(cudaError_t e, const char *what) {
 //   level_off_*    n_levels + 1 offsets into tasks
 //   q_nat          flux state in the natural layout (out / ttot), converted into out_slot
 inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tasks, const uint32_t *level_off_dev,
-                             const std::vector<uint32_t> &level_off_host, uint64_t n_tasks, uint32_t n_levels,
-                             int n_local_dirs, const double *q_nat, int num_sms, cudaStream_t stream,
-                             uint64_t *launch_counter) {
+                             uint64_t n_tasks, uint32_t n_levels, int n_local_dirs, const uint32_t *pcells,
+                             uint32_t n_periodic, const int32_t *pidx, const double *q_nat, int num_sms,
+                             cudaStream_t stream, uint64_t *launch_counter) {
     C.release();
     if (n_tasks >= 0x7fffff00ull) throw std::runtime_error("compile_schedule: more than 2^31 tasks per rank");
     if (n_local_dirs > 128) throw std::runtime_error("compile_schedule: more than 128 local directions");
     const uint32_t n = (uint32_t)n_tasks;
     const uint32_t n_dl = (uint32_t)n_local_dirs;
+    // tunables (environment overrides are for experiments; DESIGN.md section 5 lists the defaults)
+    const uint32_t threads = env_u32("SSW_STREAM_THREADS", 512) == 256 ? 256u : 512u;
+    uint32_t G = std::min<uint32_t>(env_u32("SSW_STREAM_GROUPS", 4), kMaxGroups);
+    G = std::max<uint32_t>(1u, std::min<uint32_t>(G, n_dl));
+    uint32_t want_bps = env_u32("SSW_STREAM_BPS", threads == 256 ? 4 : 2);
+    const uint32_t want_stages = std::max<uint32_t>(1u, std::min<uint32_t>(env_u32("SSW_STREAM_STAGES", 3), kMaxStages));
+    const uint32_t n_real_pl = n_levels * G, n_pl = n_real_pl + G;
+    const uint32_t n_epi_cand = n_periodic * n_dl;
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    uint32_t *keys_in = nullptr, *keys = nullptr, *cnt = nullptr, *tile_cnt = nullptr, *tile_off = nullptr,
+
+    unsigned long long *keys64_in = nullptr, *keys64 = nullptr, *epi_in = nullptr, *epi_sorted = nullptr, *upoff = nullptr,
+                       *tentry_dev = nullptr;
+    uint32_t *keys = nullptr, *cnt = nullptr, *pl_off = nullptr, *tile_cnt = nullptr, *tile_off = nullptr,
              *tile_start = nullptr, *tab_block = nullptr;
-    unsigned long long *upoff = nullptr;
-    unsigned int *counters = nullptr;   // [0] n_lag (count pass), [1] lag fill cursor
+    unsigned int *counters = nullptr;   // [0] n_lag (count pass), [1] lag fill cursor, [2] error flag
     void *temp = nullptr;
     auto cleanup = [&]() {
-        cudaFree(keys_in); cudaFree(keys); cudaFree(cnt); cudaFree(tile_cnt); cudaFree(tile_off);
-        cudaFree(tile_start); cudaFree(tab_block); cudaFree(upoff); cudaFree(counters); cudaFree(temp);
+        cudaFree(keys64_in); cudaFree(keys64); cudaFree(epi_in); cudaFree(epi_sorted); cudaFree(upoff);
+        cudaFree(tentry_dev); cudaFree(keys); cudaFree(cnt); cudaFree(pl_off); cudaFree(tile_cnt); cudaFree(tile_off);
+        cudaFree(tile_start); cudaFree(tab_block); cudaFree(counters); cudaFree(temp);
     };
     try {
-        // 1. order every level by (cell, direction)
-        cuda_ok(cudaMalloc(&keys_in, sizeof(uint32_t) * (size_t)n), "malloc keys_in");
-        cuda_ok(cudaMalloc(&keys, sizeof(uint32_t) * (size_t)n), "malloc keys");
-        s_key_kernel<<<blocks, 256, 0, stream>>>(tasks, n, g.n_cells, n_dl, keys_in);
         size_t bytes = 0;
-        cuda_ok(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, keys_in, keys, (int64_t)n, (int64_t)n_levels,
+        // 1. order every level by (group, cell, direction)
+        cuda_ok(cudaMalloc(&keys64_in, sizeof(unsigned long long) * (size_t)n), "malloc keys64_in");
+        cuda_ok(cudaMalloc(&keys64, sizeof(unsigned long long) * (size_t)n), "malloc keys64");
+        s_key64_kernel<<<blocks, 256, 0, stream>>>(tasks, n, g.n_cells, n_dl, G, keys64_in);
+        cuda_ok(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, keys64_in, keys64, (int64_t)n, (int64_t)n_levels,
                                                    level_off_dev, level_off_dev + 1, stream), "segmented sort size");
         cuda_ok(cudaMalloc(&temp, bytes), "malloc sort temp");
-        cuda_ok(cub::DeviceSegmentedSort::SortKeys(temp, bytes, keys_in, keys, (int64_t)n, (int64_t)n_levels,
+        cuda_ok(cub::DeviceSegmentedSort::SortKeys(temp, bytes, keys64_in, keys64, (int64_t)n, (int64_t)n_levels,
                                                    level_off_dev, level_off_dev + 1, stream), "segmented sort");
         cuda_ok(cudaStreamSynchronize(stream), "segmented sort sync");
         cudaFree(temp); temp = nullptr;
-        cudaFree(keys_in); keys_in = nullptr;
+        cudaFree(keys64_in); keys64_in = nullptr;
 
-        // 2. slots, entry counts, downwind areas
+        // 2. epilogue tasks: (periodic cell, direction) pairs with a periodic upwind face
+        cuda_ok(cudaMalloc(&epi_in, sizeof(unsigned long long) * (size_t)std::max<uint32_t>(n_epi_cand, 1)), "malloc epi");
+        cuda_ok(cudaMalloc(&epi_sorted, sizeof(unsigned long long) * (size_t)std::max<uint32_t>(n_epi_cand, 1)), "malloc epi");
+        if (n_epi_cand) {
+            s_epilogue_key_kernel<<<(n_epi_cand + 255) / 256, 256, 0, stream>>>(g, pcells, n_periodic, n_dl, G, epi_in);
+            cuda_ok(cub::DeviceRadixSort::SortKeys(nullptr, bytes, epi_in, epi_sorted, (int64_t)n_epi_cand, 0, 64, stream), "radix size");
+            cuda_ok(cudaMalloc(&temp, bytes), "malloc radix temp");
+            cuda_ok(cub::DeviceRadixSort::SortKeys(temp, bytes, epi_in, epi_sorted, (int64_t)n_epi_cand, 0, 64, stream), "radix sort");
+        }
+        // 3. pseudo-level offsets
+        cuda_ok(cudaMalloc(&pl_off, sizeof(uint32_t) * ((size_t)n_pl + 1)), "malloc pl_off");
+        s_pl_off_kernel<<<(n_pl + 1 + 255) / 256, 256, 0, stream>>>(keys64, level_off_dev, n_levels, G, epi_sorted, n_epi_cand,
+                                                                    n, pl_off);
+        std::vector<uint32_t> pl_off_h(n_pl + 1);
+        cuda_ok(cudaMemcpyAsync(pl_off_h.data(), pl_off, sizeof(uint32_t) * ((size_t)n_pl + 1), cudaMemcpyDeviceToHost, stream), "copy pl_off");
+        cuda_ok(cudaStreamSynchronize(stream), "pl_off sync");
+        cudaFree(temp); temp = nullptr;
+        const uint32_t n_all = pl_off_h[n_pl];
+        const uint32_t m = n_all - n;
+        if (pl_off_h[n_real_pl] != n) throw std::runtime_error("compile_schedule: pseudo-level offsets inconsistent");
+        // 32-bit keys (cell * Dl + dl) of real and epilogue slots
+        cuda_ok(cudaMalloc(&keys, sizeof(uint32_t) * (size_t)std::max<uint32_t>(n_all, 1)), "malloc keys");
+        s_key32_kernel<<<blocks, 256, 0, stream>>>(keys64, n, keys);
+        if (m) s_key32_kernel<<<(m + 255) / 256, 256, 0, stream>>>(epi_sorted, m, keys + n);
+        cuda_ok(cudaStreamSynchronize(stream), "key32 sync");
+        cudaFree(keys64); keys64 = nullptr;
+        cudaFree(epi_in); epi_in = nullptr;
+        cudaFree(epi_sorted); epi_sorted = nullptr;
+
+        // 4. slots, entry counts, downwind areas
         cuda_ok(cudaMalloc(&C.slot_of, sizeof(uint32_t) * (size_t)n), "malloc slot_of");
         cuda_ok(cudaMalloc(&C.ttot_slot, sizeof(double) * (size_t)n), "malloc ttot_slot");
-        cuda_ok(cudaMalloc(&cnt, sizeof(uint32_t) * ((size_t)n + 1)), "malloc cnt");
-        cuda_ok(cudaMalloc(&upoff, sizeof(unsigned long long) * ((size_t)n + 1)), "malloc upoff");
-        cuda_ok(cudaMalloc(&counters, 2 * sizeof(unsigned int)), "malloc counters");
-        cuda_ok(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), stream), "memset");
-        cuda_ok(cudaMemsetAsync(cnt + n, 0, sizeof(uint32_t), stream), "memset");
+        cuda_ok(cudaMalloc(&cnt, sizeof(uint32_t) * ((size_t)n_all + 1)), "malloc cnt");
+        cuda_ok(cudaMalloc(&upoff, sizeof(unsigned long long) * ((size_t)n_all + 1)), "malloc upoff");
+        cuda_ok(cudaMalloc(&counters, 4 * sizeof(unsigned int)), "malloc counters");
+        cuda_ok(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), stream), "memset");
+        cuda_ok(cudaMemsetAsync(cnt + n_all, 0, sizeof(uint32_t), stream), "memset");
         s_slot_scatter_kernel<<<blocks, 256, 0, stream>>>(keys, n, g.n_cells, n_dl, C.slot_of);
-        s_count_kernel<<<blocks, 256, 0, stream>>>(g, keys, n, n_dl, C.slot_of, level_off_dev, n_levels, cnt,
-                                                   C.ttot_slot, counters);
-        cuda_ok(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt, upoff, (int64_t)n + 1, stream), "scan size");
+        s_count_kernel<<<(n_all + 255) / 256, 256, 0, stream>>>(g, keys, n, n_all, n_dl, C.slot_of, pl_off, n_pl, cnt,
+                                                                C.ttot_slot, counters);
+        cuda_ok(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt, upoff, (int64_t)n_all + 1, stream), "scan size");
         cuda_ok(cudaMalloc(&temp, bytes), "malloc scan temp");
-        cuda_ok(cub::DeviceScan::ExclusiveSum(temp, bytes, cnt, upoff, (int64_t)n + 1, stream), "scan");
+        cuda_ok(cub::DeviceScan::ExclusiveSum(temp, bytes, cnt, upoff, (int64_t)n_all + 1, stream), "scan");
         unsigned long long total_entries = 0;
         unsigned int n_lag = 0;
-        cuda_ok(cudaMemcpyAsync(&total_entries, upoff + n, sizeof total_entries, cudaMemcpyDeviceToHost, stream), "copy");
+        cuda_ok(cudaMemcpyAsync(&total_entries, upoff + n_all, sizeof total_entries, cudaMemcpyDeviceToHost, stream), "copy");
         cuda_ok(cudaMemcpyAsync(&n_lag, counters, sizeof n_lag, cudaMemcpyDeviceToHost, stream), "copy");
         cuda_ok(cudaStreamSynchronize(stream), "count sync");
         cudaFree(temp); temp = nullptr;
@@ -555,127 +817,150 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         C.n_lag = n_lag;
         if ((uint64_t)n + n_lag >= 0x7fffff00ull) throw std::runtime_error("compile_schedule: slot index overflow");
 
-        // 3. tiles: greedy cut at segment boundaries, one warp per level
-        cuda_ok(cudaMalloc(&tile_cnt, sizeof(uint32_t) * (size_t)n_levels), "malloc tile_cnt");
-        cuda_ok(cudaMalloc(&tile_off, sizeof(uint32_t) * ((size_t)n_levels + 1)), "malloc tile_off");
-        const unsigned cut_blocks = (unsigned)(((size_t)n_levels * 32 + 127) / 128);
-        s_cut_kernel<<<cut_blocks, 128, 0, stream>>>(keys, level_off_dev, n_levels, n_dl, kStreamThreads, nullptr,
-                                                     tile_cnt, nullptr);
-        std::vector<uint32_t> tcnt(n_levels), toff(n_levels + 1, 0);
-        cuda_ok(cudaMemcpyAsync(tcnt.data(), tile_cnt, sizeof(uint32_t) * n_levels, cudaMemcpyDeviceToHost, stream), "copy");
+        // 5. tiles: greedy cut at segment boundaries, one warp per pseudo-level
+        cuda_ok(cudaMalloc(&tile_cnt, sizeof(uint32_t) * (size_t)n_pl), "malloc tile_cnt");
+        cuda_ok(cudaMalloc(&tile_off, sizeof(uint32_t) * ((size_t)n_pl + 1)), "malloc tile_off");
+        const unsigned cut_blocks = (unsigned)(((size_t)n_pl * 32 + 127) / 128);
+        s_cut_kernel<<<cut_blocks, 128, 0, stream>>>(keys, pl_off, n_pl, n_dl, threads, nullptr, tile_cnt, nullptr);
+        std::vector<uint32_t> tcnt(n_pl), toff(n_pl + 1, 0);
+        cuda_ok(cudaMemcpyAsync(tcnt.data(), tile_cnt, sizeof(uint32_t) * n_pl, cudaMemcpyDeviceToHost, stream), "copy");
         cuda_ok(cudaStreamSynchronize(stream), "cut sync");
-        for (uint32_t l = 0; l < n_levels; ++l) toff[l + 1] = toff[l] + tcnt[l];
-        const uint32_t n_tiles = toff[n_levels];
-        cuda_ok(cudaMemcpyAsync(tile_off, toff.data(), sizeof(uint32_t) * (n_levels + 1), cudaMemcpyHostToDevice, stream), "copy");
+        for (uint32_t l = 0; l < n_pl; ++l) toff[l + 1] = toff[l] + tcnt[l];
+        const uint32_t n_tiles = toff[n_pl];
+        cuda_ok(cudaMemcpyAsync(tile_off, toff.data(), sizeof(uint32_t) * ((size_t)n_pl + 1), cudaMemcpyHostToDevice, stream), "copy");
         cuda_ok(cudaMalloc(&tile_start, sizeof(uint32_t) * ((size_t)n_tiles + 1)), "malloc tile_start");
-        s_cut_kernel<<<cut_blocks, 128, 0, stream>>>(keys, level_off_dev, n_levels, n_dl, kStreamThreads, tile_off,
-                                                     nullptr, tile_start);
+        s_cut_kernel<<<cut_blocks, 128, 0, stream>>>(keys, pl_off, n_pl, n_dl, threads, tile_off, nullptr, tile_start);
         std::vector<uint32_t> tstart(n_tiles + 1);
-        cuda_ok(cudaMemcpyAsync(tstart.data(), tile_start, sizeof(uint32_t) * n_tiles, cudaMemcpyDeviceToHost, stream), "copy");
-        cuda_ok(cudaStreamSynchronize(stream), "cut sync 2");
-        tstart[n_tiles] = n;
-        // entry offsets at the tile starts
         std::vector<unsigned long long> tentry(n_tiles + 1);
-        unsigned long long *tentry_dev = nullptr;
         cuda_ok(cudaMalloc(&tentry_dev, sizeof(unsigned long long) * ((size_t)n_tiles + 1)), "malloc tentry");
-        s_gather_offsets_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, stream>>>(upoff, tile_start, n_tiles, n, tentry_dev);
-        cudaError_t ce = cudaMemcpyAsync(tentry.data(), tentry_dev, sizeof(unsigned long long) * ((size_t)n_tiles + 1),
-                                         cudaMemcpyDeviceToHost, stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream);
-        cudaFree(tentry_dev);
-        cuda_ok(ce, "tile entry gather");
+        s_gather_offsets_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, stream>>>(upoff, tile_start, n_tiles, n_all, tentry_dev);
+        cuda_ok(cudaMemcpyAsync(tstart.data(), tile_start, sizeof(uint32_t) * n_tiles, cudaMemcpyDeviceToHost, stream), "copy");
+        cuda_ok(cudaMemcpyAsync(tentry.data(), tentry_dev, sizeof(unsigned long long) * ((size_t)n_tiles + 1),
+                                cudaMemcpyDeviceToHost, stream), "copy");
+        cuda_ok(cudaStreamSynchronize(stream), "cut sync 2");
+        tstart[n_tiles] = n_all;
 
-        // 4. launch geometry: stage size = largest packet; blocks per SM and stages from the smem budget
+        // 6. launch geometry: stage size = largest packet; blocks per SM and stages from the smem budget
         uint32_t max_bytes = 0;
-        std::vector<uint32_t> tlevel(n_tiles);
-        for (uint32_t l = 0; l < n_levels; ++l)
-            for (uint32_t t = toff[l]; t < toff[l + 1]; ++t) tlevel[t] = l;
         for (uint32_t t = 0; t < n_tiles; ++t) {
             const uint32_t ns = tstart[t + 1] - tstart[t];
             const unsigned long long E = tentry[t + 1] - tentry[t];
-            if (ns > (uint32_t)kStreamThreads || E > 65535ull)
-                throw std::runtime_error("compile_schedule: tile too large (more than 65535 upwind entries in 512 tasks)");
+            if (ns > threads || E > 65535ull)
+                throw std::runtime_error("compile_schedule: tile too large (more than 65535 upwind entries in one tile)");
             max_bytes = std::max(max_bytes, tile_layout(ns, (uint32_t)E).bytes);
         }
-        const uint32_t stage_bytes = (max_bytes + 127u) & ~127u;
-        const size_t smem_cap = 227u * 1024u;
-        uint32_t blocks_per_sm = 2, stages = 0;
-        for (; blocks_per_sm >= 1; --blocks_per_sm) {
-            const size_t per_block = smem_cap / blocks_per_sm - 1024;   // 1 KB reserved per block by the driver
+        const uint32_t stage_bytes = std::max<uint32_t>(128u, (max_bytes + 127u) & ~127u);
+        const size_t smem_sm = 227u * 1024u;
+        uint32_t bps = std::max<uint32_t>(1u, want_bps), stages = 0;
+        for (;; --bps) {
+            const size_t per_block = smem_sm / bps - 1024 - 1024;   // driver reserve + static shared memory
             const size_t fixed = stream_smem_bytes(0, 0);
-            if (per_block < fixed + stage_bytes) { if (blocks_per_sm == 1) break; continue; }
-            stages = (uint32_t)std::min<size_t>(kMaxStages, (per_block - fixed) / stage_bytes);
-            if (stages >= 2 || blocks_per_sm == 1) break;
+            if (per_block >= fixed + stage_bytes) {
+                stages = (uint32_t)std::min<size_t>(want_stages, (per_block - fixed) / stage_bytes);
+                if (stages >= 2 || bps == 1) break;
+            }
+            if (bps == 1) break;
         }
         if (stages < 1) throw std::runtime_error("compile_schedule: a tile packet does not fit in shared memory");
+        StreamKernel kernel = stream_kernel_for(threads, bps);
+        const size_t smem = stream_smem_bytes(stages, stage_bytes);
+        cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "set max dynamic smem");
+        int per_sm = 0;
+        cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)threads, smem), "occupancy");
+        if (per_sm < 1) throw std::runtime_error("compile_schedule: stream kernel does not fit on an SM");
+        uint32_t nb = (uint32_t)std::min<int>(per_sm, (int)bps) * (uint32_t)num_sms;
+        nb -= nb % G;
+        if (nb < G) throw std::runtime_error("compile_schedule: fewer blocks than direction groups");
+        const uint32_t nb_g = nb / G;
+        C.threads = threads;
+        C.bps = bps;
         C.stages = stages;
         C.stage_bytes = stage_bytes;
-        const size_t smem = stream_smem_bytes(stages, stage_bytes);
-        cuda_ok(cudaFuncSetAttribute(sweep_stream_kernel<kStreamThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem), "set max dynamic smem");
-        int per_sm = 0;
-        cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_stream_kernel<kStreamThreads>,
-                                                              kStreamThreads, smem), "occupancy");
-        if (per_sm < 1) throw std::runtime_error("compile_schedule: stream kernel does not fit on an SM");
-        C.n_blocks = (uint32_t)std::min<int>(per_sm, (int)blocks_per_sm) * (uint32_t)num_sms;
-        const uint32_t nb = C.n_blocks;
+        C.n_blocks = nb;
 
-        // 5. tile table (block-major), per-block streams, per-level barrier targets
+        // 7. tile table (block-major), per-block streams, barrier targets and dependencies
+        std::vector<uint32_t> tile_block(n_tiles), tile_level(n_tiles), per_block_count(nb, 0), rr(G, 0);
+        for (uint32_t pl = 0; pl < n_pl; ++pl) {
+            const uint32_t grp = pl < n_real_pl ? pl % G : pl - n_real_pl;
+            for (uint32_t t = toff[pl]; t < toff[pl + 1]; ++t) {
+                const uint32_t b = grp + (rr[grp]++ % nb_g) * G;
+                tile_block[t] = b;
+                tile_level[t] = pl;
+                per_block_count[b]++;
+            }
+        }
         std::vector<uint32_t> tab_off(nb + 1, 0);
-        for (uint32_t b = 0; b < nb; ++b) tab_off[b + 1] = tab_off[b] + (n_tiles > b ? (n_tiles - b + nb - 1) / nb : 0);
-        std::vector<TileDesc> tab(n_tiles);
-        std::vector<uint32_t> tab_block_h(n_tiles);
-        std::vector<uint64_t> stream_off(nb + 1, 0);
-        std::vector<uint64_t> cursor(nb, 0);
+        for (uint32_t b = 0; b < nb; ++b) tab_off[b + 1] = tab_off[b] + per_block_count[b];
+        std::vector<TileDesc> tab(std::max<uint32_t>(n_tiles, 1));
+        std::vector<uint32_t> tab_block_h(std::max<uint32_t>(n_tiles, 1));
+        std::vector<uint64_t> stream_off(nb + 1, 0), cursor(nb, 0);
+        std::vector<uint32_t> fill_pos(nb, 0);
         for (uint32_t t = 0; t < n_tiles; ++t) {
-            const uint32_t b = t % nb, k = t / nb;
+            const uint32_t b = tile_block[t];
             TileDesc d;
             d.slot0 = tstart[t];
             d.n = (uint16_t)(tstart[t + 1] - tstart[t]);
             d.n_entries = (uint16_t)(tentry[t + 1] - tentry[t]);
-            d.level = tlevel[t];
+            d.level = tile_level[t];
             if ((cursor[b] >> 4) > 0xffffffffull) throw std::runtime_error("compile_schedule: block stream exceeds 64 GB");
             d.off16 = (uint32_t)(cursor[b] >> 4);
             cursor[b] += tile_layout(d.n, d.n_entries).bytes;
-            tab[tab_off[b] + k] = d;
-            tab_block_h[tab_off[b] + k] = b;
+            tab[tab_off[b] + fill_pos[b]] = d;
+            tab_block_h[tab_off[b] + fill_pos[b]] = b;
+            fill_pos[b]++;
         }
         for (uint32_t b = 0; b < nb; ++b) stream_off[b + 1] = stream_off[b] + ((cursor[b] + 127u) & ~(uint64_t)127u);
         C.stream_bytes = stream_off[nb];
-        std::vector<uint32_t> lvl_target(n_levels);
-        for (uint32_t l = 0; l < n_levels; ++l) lvl_target[l] = std::min<uint32_t>(tcnt[l], nb);
+        std::vector<uint32_t> lvl_target(n_pl), lvl_dep(n_pl, kNoDep);
+        for (uint32_t pl = 0; pl < n_pl; ++pl) lvl_target[pl] = std::min<uint32_t>(tcnt[pl], nb_g);
+        for (uint32_t pl = G; pl < n_real_pl; ++pl) lvl_dep[pl] = pl - G;
+        for (uint32_t grp = 0; grp < G; ++grp) {   // epilogue: behind the group's last non-empty wavefront level
+            for (uint32_t l = n_levels; l-- > 0;) {
+                if (tcnt[l * G + grp] > 0) { lvl_dep[n_real_pl + grp] = l * G + grp; break; }
+            }
+        }
         C.n_tiles = n_tiles;
 
-        cuda_ok(cudaMalloc(&C.stream, std::max<uint64_t>(C.stream_bytes, 16)), "malloc stream");
-        cuda_ok(cudaMalloc(&C.tab, sizeof(TileDesc) * (size_t)n_tiles), "malloc tab");
-        cuda_ok(cudaMalloc(&tab_block, sizeof(uint32_t) * (size_t)n_tiles), "malloc tab_block");
+        cuda_ok(cudaMalloc(&C.stream, std::max<uint64_t>(C.stream_bytes, 128)), "malloc stream");
+        cuda_ok(cudaMalloc(&C.tab, sizeof(TileDesc) * tab.size()), "malloc tab");
+        cuda_ok(cudaMalloc(&tab_block, sizeof(uint32_t) * tab_block_h.size()), "malloc tab_block");
         cuda_ok(cudaMalloc(&C.tab_off, sizeof(uint32_t) * ((size_t)nb + 1)), "malloc tab_off");
         cuda_ok(cudaMalloc(&C.stream_off, sizeof(uint64_t) * ((size_t)nb + 1)), "malloc stream_off");
-        cuda_ok(cudaMalloc(&C.lvl_target, sizeof(uint32_t) * (size_t)n_levels), "malloc lvl_target");
-        cuda_ok(cudaMalloc(&C.lvl_count, sizeof(unsigned int) * (size_t)n_levels), "malloc lvl_count");
+        cuda_ok(cudaMalloc(&C.lvl_target, sizeof(uint32_t) * (size_t)n_pl), "malloc lvl_target");
+        cuda_ok(cudaMalloc(&C.lvl_dep, sizeof(uint32_t) * (size_t)n_pl), "malloc lvl_dep");
+        cuda_ok(cudaMalloc(&C.lvl_count, sizeof(unsigned int) * (size_t)n_pl), "malloc lvl_count");
         cuda_ok(cudaMalloc(&C.out_slot, sizeof(double) * ((size_t)n + n_lag)), "malloc out_slot");
         cuda_ok(cudaMalloc(&C.lag_src, sizeof(uint32_t) * (size_t)std::max<uint32_t>(n_lag, 1)), "malloc lag_src");
-        cuda_ok(cudaMemcpyAsync(C.tab, tab.data(), sizeof(TileDesc) * (size_t)n_tiles, cudaMemcpyHostToDevice, stream), "copy tab");
-        cuda_ok(cudaMemcpyAsync(tab_block, tab_block_h.data(), sizeof(uint32_t) * (size_t)n_tiles, cudaMemcpyHostToDevice, stream), "copy");
+        cuda_ok(cudaMalloc(&C.acc_cell, sizeof(double) * (size_t)G * g.n_cells), "malloc acc_cell");
+        cuda_ok(cudaMalloc(&C.acc_per, sizeof(double) * (size_t)G * std::max<uint32_t>(n_periodic, 1)), "malloc acc_per");
+        cuda_ok(cudaMemcpyAsync(C.tab, tab.data(), sizeof(TileDesc) * tab.size(), cudaMemcpyHostToDevice, stream), "copy tab");
+        cuda_ok(cudaMemcpyAsync(tab_block, tab_block_h.data(), sizeof(uint32_t) * tab_block_h.size(), cudaMemcpyHostToDevice, stream), "copy");
         cuda_ok(cudaMemcpyAsync(C.tab_off, tab_off.data(), sizeof(uint32_t) * ((size_t)nb + 1), cudaMemcpyHostToDevice, stream), "copy");
         cuda_ok(cudaMemcpyAsync(C.stream_off, stream_off.data(), sizeof(uint64_t) * ((size_t)nb + 1), cudaMemcpyHostToDevice, stream), "copy");
-        cuda_ok(cudaMemcpyAsync(C.lvl_target, lvl_target.data(), sizeof(uint32_t) * (size_t)n_levels, cudaMemcpyHostToDevice, stream), "copy");
+        cuda_ok(cudaMemcpyAsync(C.lvl_target, lvl_target.data(), sizeof(uint32_t) * (size_t)n_pl, cudaMemcpyHostToDevice, stream), "copy");
+        cuda_ok(cudaMemcpyAsync(C.lvl_dep, lvl_dep.data(), sizeof(uint32_t) * (size_t)n_pl, cudaMemcpyHostToDevice, stream), "copy");
 
-        // 6. packets and state
-        FillArgs fa;
-        fa.g = g; fa.keys = keys; fa.slot_of = C.slot_of; fa.upoff = upoff; fa.ttot_slot = C.ttot_slot;
-        fa.level_off = level_off_dev; fa.n_levels = n_levels; fa.n_dl = n_dl; fa.n_tasks = n;
-        fa.tab = C.tab; fa.tab_block = tab_block; fa.stream_off = C.stream_off; fa.stream = C.stream;
-        fa.lag_src = C.lag_src; fa.lag_counter = counters + 1;
-        s_fill_kernel<<<n_tiles, kStreamThreads, 0, stream>>>(fa);
+        // 8. packets and state
+        if (n_tiles) {
+            FillArgs fa;
+            fa.g = g; fa.keys = keys; fa.slot_of = C.slot_of; fa.pidx = pidx; fa.upoff = upoff; fa.ttot_slot = C.ttot_slot;
+            fa.pl_off = pl_off; fa.n_pl = n_pl; fa.n_real_pl = n_real_pl; fa.n_dl = n_dl; fa.n_tasks = n;
+            fa.tab = C.tab; fa.tab_block = tab_block; fa.tab_off = C.tab_off; fa.stream_off = C.stream_off;
+            fa.stream = C.stream; fa.lag_src = C.lag_src; fa.lag_counter = counters + 1; fa.stages = stages;
+            fa.lvl_dep = C.lvl_dep; fa.lvl_target = C.lvl_target;
+            s_fill_kernel<<<n_tiles, kMaxStreamThreads, 0, stream>>>(fa);
+        }
         s_convert_state_kernel<<<blocks, 256, 0, stream>>>(keys, n, g.n_cells, n_dl, q_nat, C.ttot_slot, C.out_slot);
         cuda_ok(cudaGetLastError(), "compile kernels");
         unsigned int lag_filled = 0;
         cuda_ok(cudaMemcpyAsync(&lag_filled, counters + 1, sizeof lag_filled, cudaMemcpyDeviceToHost, stream), "copy");
         cuda_ok(cudaStreamSynchronize(stream), "compile sync");   // host vectors go out of scope
         if (lag_filled != n_lag) throw std::runtime_error("compile_schedule: periodic snapshot count mismatch");
-        if (launch_counter) *launch_counter += 11;
-        (void)level_off_host;
+        unsigned int too_many = 0;
+        cuda_ok(cudaMemcpy(&too_many, counters + 2, sizeof too_many, cudaMemcpyDeviceToHost), "copy");
+        if (too_many) throw std::runtime_error("compile_schedule: a task has more than 255 periodic upwind faces");
+        if (launch_counter) *launch_counter += 14;
+        C.n_epilogue = m;
     } catch (...) {
         cleanup();
         C.release();
@@ -684,41 +969,75 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
     cleanup();
     C.n_tasks = n_tasks;
     C.n_levels = n_levels;
+    C.n_groups = G;
+    C.n_pl = n_pl;
+    C.n_cells = g.n_cells;
+    C.n_periodic = n_periodic;
     C.mean_entries = n_tasks ? (double)C.n_entries / (double)n_tasks : 0.0;
     C.valid = true;
 }
 
-// One all-cells sweep (solve = 1) or one evaluation of sum_d incoming (solve = 0) over the compiled schedule.
-inline void run_compiled(Compiled &C, const double2 *cellrec, double *rate_cell, uint32_t n_cells, double threshold,
-                         int solve, cudaStream_t stream, uint64_t *launch_counter) {
+// One all-cells sweep (solve = 1) or one evaluation of sum_d incoming (solve = 0) over the compiled
+// schedule.  Leaves the per-group sums in C.acc_cell / C.acc_per (s_rate_finish_kernel folds them).
+inline void run_compiled(Compiled &C, const double2 *cellrec, double threshold, int solve, cudaStream_t stream,
+                         uint64_t *launch_counter) {
     StreamArgs a;
     a.stream = C.stream;
     a.stream_off = C.stream_off;
     a.tab = C.tab;
     a.tab_off = C.tab_off;
     a.lvl_target = C.lvl_target;
+    a.lvl_dep = C.lvl_dep;
     a.lvl_count = C.lvl_count;
     a.out_slot = C.out_slot;
     a.cellrec = cellrec;
-    a.rate_cell = rate_cell;
+    a.acc_cell = C.acc_cell;
+    a.acc_per = C.acc_per;
     a.threshold = threshold;
     a.stages = C.stages;
     a.stage_bytes = C.stage_bytes;
+    a.n_groups = C.n_groups;
+    a.n_real_pl = C.n_levels * C.n_groups;
+    a.n_cells = C.n_cells;
+    a.n_periodic = C.n_periodic;
     a.solve = solve;
-    cuda_ok(cudaMemsetAsync(C.lvl_count, 0, sizeof(unsigned int) * (size_t)C.n_levels, stream), "memset lvl_count");
-    cuda_ok(cudaMemsetAsync(rate_cell, 0, sizeof(double) * (size_t)n_cells, stream), "memset rate_cell");
+    a.prof = nullptr;
+    unsigned long long *prof_dev = nullptr;
+    if (env_u32("SSW_STREAM_PROFILE", 0)) {
+        cuda_ok(cudaMalloc(&prof_dev, sizeof(unsigned long long) * 4 * (size_t)C.n_blocks), "malloc prof");
+        cuda_ok(cudaMemsetAsync(prof_dev, 0, sizeof(unsigned long long) * 4 * (size_t)C.n_blocks, stream), "memset prof");
+        a.prof = prof_dev;
+    }
+    cuda_ok(cudaMemsetAsync(C.lvl_count, 0, sizeof(unsigned int) * (size_t)C.n_pl, stream), "memset lvl_count");
+    cuda_ok(cudaMemsetAsync(C.acc_cell, 0, sizeof(double) * (size_t)C.n_groups * C.n_cells, stream), "memset acc_cell");
+    if (C.n_periodic)
+        cuda_ok(cudaMemsetAsync(C.acc_per, 0, sizeof(double) * (size_t)C.n_groups * C.n_periodic, stream), "memset acc_per");
     uint64_t launches = 1;
     if (solve && C.n_lag) {
         s_lag_snapshot_kernel<<<(C.n_lag + 255) / 256, 256, 0, stream>>>(C.lag_src, C.n_lag, (uint32_t)C.n_tasks, C.out_slot);
         ++launches;
     }
-    cuda_ok(cudaFuncSetAttribute(sweep_stream_kernel<kStreamThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)stream_smem_bytes(C.stages, C.stage_bytes)), "set max dynamic smem");
+    StreamKernel kernel = stream_kernel_for(C.threads, C.bps, prof_dev != nullptr);
+    const size_t smem = stream_smem_bytes(C.stages, C.stage_bytes);
+    cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "set max dynamic smem");
     void *args[] = {&a};
-    // cooperative launch only to guarantee co-residency of all blocks (the level barrier spins)
-    cuda_ok(cudaLaunchCooperativeKernel((const void *)sweep_stream_kernel<kStreamThreads>, dim3(C.n_blocks),
-                                        dim3(kStreamThreads), args, stream_smem_bytes(C.stages, C.stage_bytes), stream),
+    // cooperative launch only to guarantee co-residency of all blocks (the level barriers spin)
+    cuda_ok(cudaLaunchCooperativeKernel((const void *)kernel, dim3(C.n_blocks), dim3(C.threads), args, smem, stream),
             "sweep_stream_kernel launch");
+    if (prof_dev) {   // experiments only: where do the blocks spend their cycles?
+        std::vector<unsigned long long> h(4 * (size_t)C.n_blocks);
+        cudaMemcpyAsync(h.data(), prof_dev, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, stream);
+        cudaStreamSynchronize(stream);
+        cudaFree(prof_dev);
+        double tot = 0, bar = 0, pkt = 0, tiles = 0, tmax = 0;
+        for (uint32_t b = 0; b < C.n_blocks; ++b) {
+            tot += (double)h[4 * b]; bar += (double)h[4 * b + 1]; pkt += (double)h[4 * b + 2]; tiles += (double)h[4 * b + 3];
+            tmax = std::max(tmax, (double)h[4 * b]);
+        }
+        fprintf(stderr, "[stream profile] blocks %u tiles %.0f  cycles/block mean %.0f max %.0f  barrier %.1f%%  packet wait %.1f%%  "
+                        "cycles per tile (excl. barrier) %.0f  pseudo-levels %u\n",
+                C.n_blocks, tiles, tot / C.n_blocks, tmax, 100.0 * bar / tot, 100.0 * pkt / tot, (tot - bar) / tiles, C.n_pl);
+    }
     if (launch_counter) *launch_counter += launches;
 }
 

@@ -132,7 +132,7 @@ struct Sweep {
     DevBuf<uint8_t> flags;
     DevBuf<uint8_t> cub_temp;
     DevBuf<uint32_t> n_selected;
-    DevBuf<double> rate_act, cell_tmp, cell_tmp2, rate_cell;
+    DevBuf<double> rate_act, cell_tmp, cell_tmp2;
     DevBuf<double2> cellrec;
     DevBuf<unsigned long long> hist;
     DevBuf<ChemStats> chem_stats;
@@ -412,7 +412,6 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     flags.alloc(N);
     n_selected.alloc(1);
     rate_act.alloc(N);
-    rate_cell.alloc(N);
     cellrec.alloc(N);
     cell_tmp.alloc(N);
     cell_tmp2.alloc(N);
@@ -579,8 +578,8 @@ void Sweep::single_sweep(int cur) {
         if (use_compiled && !S.compiled.valid) {
             const size_t t_sched = tic(T_SCHED);
             try {
-                compile_schedule(S.compiled, grid_view(), S.tasks.p, S.level_off.p, S.level_off_host, S.n_tasks,
-                                 S.n_levels, Dl, q.p, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
+                compile_schedule(S.compiled, grid_view(), S.tasks.p, S.level_off.p, S.n_tasks, S.n_levels, Dl,
+                                 pcells.p, n_periodic, pidx.p, q.p, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
             } catch (const std::exception &e) {
                 fail(SSW_E_CUDA, "%s", e.what());
             }
@@ -594,8 +593,8 @@ void Sweep::single_sweep(int cur) {
             try {
                 cellrec_kernel<<<cdiv(N, 256), 256, 0, stream>>>(att.p, src.p, (double)D, N, cellrec.p);
                 launched();
-                run_compiled(S.compiled, cellrec.p, rate_cell.p, N, P.significant_rate_threshold_per_s, /*solve=*/1,
-                             stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
+                run_compiled(S.compiled, cellrec.p, P.significant_rate_threshold_per_s, /*solve=*/1, stream,
+                             &stat[SSW_STAT_KERNEL_LAUNCHES]);
             } catch (const std::exception &e) {
                 fail(SSW_E_CUDA, "%s", e.what());
             }
@@ -621,13 +620,18 @@ void Sweep::single_sweep(int cur) {
 
     // update_chemistry (src/sweep/mod.rs:549-574)
     const size_t t_chem = tic(T_CHEM);
-    gather_periodic(per_new.p);
     const uint32_t *act = all ? nullptr : S.act_list.p;
-    if (use_compiled && S.compiled.valid)
-        rate_finish_kernel<<<cdiv(N, 256), 256, 0, stream>>>(N, Dl, rate_cell.p, pidx.p, per_new.p, n_periodic, rate_act.p);
-    else
+    if (use_compiled && S.compiled.valid) {
+        // the compiled sweep left sum_d incoming and sum_d periodic_source in its group accumulators
+        const Compiled &C = S.compiled;
+        s_rate_finish_kernel<<<cdiv(N, 256), 256, 0, stream>>>(N, C.n_groups, n_periodic, Dl, (double)D, C.acc_cell,
+                                                               C.acc_per, pidx.p, src.p, rate_act.p, nullptr);
+    } else {
+        gather_periodic(per_new.p);
+        launched();
         rate_kernel<<<cdiv(n_act, 256), 256, 0, stream>>>(act, n_act, N, Dl, incoming.p, pidx.p, per_new.p,
                                                           n_periodic, rate_act.p);
+    }
     launched();
     maybe_allreduce(rate_act.p, n_act);
     ChemParams cp;
@@ -712,7 +716,20 @@ void Sweep::read_field(int field, double *out) {
     case SSW_F_SOURCE: srcp = src.p; break;
     case SSW_F_IONIZATION_TIME: srcp = ion_time.p; break;
     case SSW_F_PHOTON_RATE:
-        dir_state_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), state_view(), 0, Dl, nullptr, cell_tmp.p);
+        if (state && state->valid) {
+            // sum_d incoming over the compiled schedule (evaluation only, nothing is solved)
+            try {
+                run_compiled(*state, cellrec.p, P.significant_rate_threshold_per_s, /*solve=*/0, stream,
+                             &stat[SSW_STAT_KERNEL_LAUNCHES]);
+            } catch (const std::exception &e) {
+                fail(SSW_E_CUDA, "%s", e.what());
+            }
+            s_rate_finish_kernel<<<cdiv(N, 256), 256, 0, stream>>>(N, state->n_groups, n_periodic, Dl, (double)D,
+                                                                   state->acc_cell, state->acc_per, pidx.p, src.p,
+                                                                   nullptr, cell_tmp.p);
+        } else {
+            dir_state_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), state_view(), 0, Dl, nullptr, cell_tmp.p);
+        }
         launched();
         maybe_allreduce(cell_tmp.p, N);
         srcp = cell_tmp.p;
