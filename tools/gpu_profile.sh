@@ -4,7 +4,7 @@
 # usage: tools/gpu_profile.sh <tag> [kernel-regex]
 set -u
 TAG=${1:-r1}
-KREGEX=${2:-sweep_compiled}
+KREGEX=${2:-sweep_stream_kernel}
 OUT=gpurun_out
 mkdir -p $OUT
 python -m subsweep_b200.build >/dev/null
