@@ -101,7 +101,7 @@ typedef enum ssw_field {
     SSW_F_PREVIOUS_RATE = 9,      /* Site::previous_incoming_total_rate                          */
     SSW_F_DENSITY = 10,
     SSW_F_SOURCE = 11,
-    SSW_F_IONIZATION_TIME = 12    /* ionization_time (src/sweep/mod.rs:731-738); NaN = not yet   */
+    SSW_F_IONIZATION_TIME = 12    /* ionization_time (src/sweep/mod.rs:731-738); +inf = not yet  */
 } ssw_field;
 
 /* all-reduce hook for direction sharding: sum `n` doubles in place over all ranks.  `buf` is a

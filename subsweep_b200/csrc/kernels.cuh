@@ -295,11 +295,22 @@ sweep_replay_kernel(SweepArgs a, const uint32_t *__restrict__ queue,
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 periodic_gather_kernel(GridView g, const uint32_t *__restrict__ pcells, uint32_t n_periodic,
-                       StateView st, double *__restrict__ dst) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+                       const uint32_t *__restrict__ act_list, uint32_t n_act,
+                       const int32_t *__restrict__ pidx, StateView st, double *__restrict__ dst) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     const int dl = blockIdx.y;
-    if (p >= n_periodic) return;
-    const uint32_t c = pcells[p];
+    uint32_t c, p;
+    if (act_list) {   // partial active set: only the rows the tasks of this sweep read
+        if (k >= n_act) return;
+        c = act_list[k];
+        const int32_t pp = pidx[c];
+        if (pp < 0) return;
+        p = (uint32_t)pp;
+    } else {
+        if (k >= n_periodic) return;
+        p = k;
+        c = pcells[p];
+    }
     const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
     double acc = 0.0;
     for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
@@ -337,6 +348,43 @@ dir_state_kernel(GridView g, StateView st, int which, int n_local_dirs,
         total += acc;
     }
     if (photon_rate) photon_rate[c] = total;
+}
+
+// photon_rate bookkeeping for partial active sets (src/sweep/mod.rs:487-503, 727-730): a sweep over
+// the active set A changes incoming_total_rate of every Local neighbour of A, active or not.
+// mark_touched_kernel flags those neighbours; photon_patch_kernel re-evaluates sum_d incoming[d]
+// for them -- one block per touched cell, one thread per local direction, summed in direction order.
+__global__ void __launch_bounds__(256)
+mark_touched_kernel(GridView g, const uint32_t *__restrict__ act_list, uint32_t n_act, uint8_t *__restrict__ flags) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_act) return;
+    const uint32_t c = act_list[k];
+    for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f)
+        if (g.face_kind[f] == 0) flags[g.face_nb[f]] = 1;
+}
+
+__global__ void __launch_bounds__(kMaxDirs)
+photon_patch_kernel(GridView g, StateView st, const uint32_t *__restrict__ touch_list, int n_local_dirs,
+                    double *__restrict__ photon) {
+    __shared__ double s_in[kMaxDirs];
+    const uint32_t c = touch_list[blockIdx.x];
+    const int dl = threadIdx.x;
+    if (dl < n_local_dirs) {
+        const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+        double acc = 0.0;
+        for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
+            if (g.face_kind[f] != 0) continue;
+            const double d = dot_dir(ld_geo(g.face_geo + f), dx, dy, dz);
+            if (d < 0.0) acc += st.load_q(dl, (uint32_t)g.face_nb[f]) * (__ldg(g.face_rev + f) * (-d));
+        }
+        s_in[dl] = acc;
+    }
+    __syncthreads();
+    if (dl == 0) {
+        double total = 0.0;
+        for (int k = 0; k < n_local_dirs; ++k) total += s_in[k];
+        photon[c] = total;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -505,11 +553,11 @@ histogram_kernel(const uint8_t *__restrict__ level, uint32_t n, unsigned long lo
     if (threadIdx.x < 32 && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
 }
 
-// ionization_time (src/sweep/mod.rs:731-738): first time xHII > 0.5
+// ionization_time (src/sweep/mod.rs:731-738): first time xHII > 0.5; +inf = IonizationTime::default() = not yet
 __global__ void __launch_bounds__(256)
 ionization_time_kernel(const double *__restrict__ x, double *__restrict__ ion_time, uint32_t n, double now) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n && x[c] > 0.5 && isnan(ion_time[c])) ion_time[c] = now;
+    if (c < n && x[c] > 0.5 && isinf(ion_time[c])) ion_time[c] = now;
 }
 
 // optional chemistry outputs, src/sweep/chemistry_output.rs:25-55 with Sweep::get_solver (mod.rs:612-632)

@@ -82,7 +82,7 @@ struct PacketHeader {
     uint32_t level;
     uint32_t next_off16, next_bytes;   // packet of the tile `stages` positions later (bytes = 0: none)
     uint32_t dep, dep_target;          // pseudo-level to wait for (kNoDep: none) and its arrival count
-    uint16_t scan_steps, pad;          // shuffle steps the longest segment of the tile needs
+    uint16_t scan_steps, group;        // shuffle steps the longest segment of the tile needs; direction group
 };
 static_assert(sizeof(PacketHeader) == 32, "packet header is 32 bytes");
 
@@ -279,11 +279,13 @@ s_count_kernel(GridView g, const uint32_t *__restrict__ keys, uint32_t n, uint32
 // slots that ends at a segment (cell) boundary.  Without tile_start only counts.
 __global__ void __launch_bounds__(128)
 s_cut_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pl_off, uint32_t n_pl, uint32_t n_dl,
-             uint32_t max_slots, const uint32_t *__restrict__ tile_off, uint32_t *__restrict__ tile_cnt,
+             uint32_t max_slots_uniform, const uint32_t *__restrict__ max_slots_pl,
+             const uint32_t *__restrict__ tile_off, uint32_t *__restrict__ tile_cnt,
              uint32_t *__restrict__ tile_start) {
     const uint32_t l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (l >= n_pl) return;
+    const uint32_t max_slots = max_slots_pl ? max_slots_pl[l] : max_slots_uniform;
     const uint32_t end = pl_off[l + 1];
     uint32_t start = pl_off[l], count = 0;
     const uint32_t out = tile_start ? tile_off[l] : 0;
@@ -321,7 +323,7 @@ struct FillArgs {
     const unsigned long long *upoff;   // n_all + 1
     const double *ttot_slot;
     const uint32_t *pl_off;
-    uint32_t n_pl, n_real_pl, n_dl, n_tasks;
+    uint32_t n_pl, n_real_pl, n_dl, n_tasks, n_groups;
     const TileDesc *tab;          // block-major
     const uint32_t *tab_block;    // block of tile i (block-major index)
     const uint32_t *tab_off;      // per block
@@ -406,7 +408,8 @@ s_fill_kernel(FillArgs a) {
         info[d.n] = d.n_entries;
         PacketHeader h;
         h.slot0 = d.slot0; h.n = d.n; h.n_entries = d.n_entries; h.level = d.level;
-        h.next_off16 = 0; h.next_bytes = 0; h.pad = 0;
+        h.next_off16 = 0; h.next_bytes = 0;
+        h.group = (uint16_t)(epilogue ? d.level - a.n_real_pl : d.level % a.n_groups);
         h.dep = a.lvl_dep[d.level];
         h.dep_target = h.dep != kNoDep ? a.lvl_target[h.dep] : 0u;
         uint32_t steps = 0;
@@ -497,6 +500,13 @@ __device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p) {
     return v;
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// level counters sit one per 32-byte sector so that pollers of different pseudo-levels do not share a sector
+constexpr uint32_t kCountStride = 8;
 
 struct StreamArgs {
     const unsigned char *stream;
@@ -514,7 +524,8 @@ struct StreamArgs {
     uint32_t stages, stage_bytes;
     uint32_t n_groups, n_real_pl, n_cells, n_periodic;
     int solve;                // 1: sweep; 0: only accumulate sum_d incoming (photon_rate read-out)
-    unsigned long long *prof; // optional per-block cycle counters {total, level barrier, packet wait, tiles}
+    uint32_t poll_ns;         // back-off between polls of a level counter
+    unsigned long long *prof; // optional per-block cycle counters {total, wait behind arrive, packet wait, tiles, dependency poll, arrive}
 };
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -538,9 +549,6 @@ sweep_stream_kernel(StreamArgs a) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t n_my = a.tab_off[blockIdx.x + 1] - a.tab_off[blockIdx.x];
     const unsigned char *const stream = a.stream + a.stream_off[blockIdx.x];
-    const uint32_t grp = blockIdx.x % a.n_groups;
-    double *const acc_cell = a.acc_cell + (size_t)grp * a.n_cells;
-    double *const acc_per = a.acc_per + (size_t)grp * a.n_periodic;
     double *const out_slot = a.out_slot;
     const uint32_t n_real_pl = a.n_real_pl;
     const int solve = a.solve;
@@ -565,7 +573,7 @@ sweep_stream_kernel(StreamArgs a) {
     }
     uint32_t prev_level = kNoDep;
     uint32_t stage = 0, parity = 0;
-    long long t_begin = 0, t_bar = 0, t_pkt = 0, tp = 0;
+    long long t_begin = 0, t_bar = 0, t_pkt = 0, t_rel = 0, tp = 0;
     if (PROFILE && tid == 0) t_begin = clock64();
     for (uint32_t k = 0; k < n_my; ++k) {
         if (PROFILE && tid == 0) tp = clock64();
@@ -575,20 +583,27 @@ sweep_stream_kernel(StreamArgs a) {
         const PacketHeader d = *reinterpret_cast<const PacketHeader *>(pkt);
         if (d.level != prev_level) {
             __syncthreads();   // every thread has issued all its stores of the previous pseudo-level
-            if (tid == 0) {
+            // arrive (thread 0) and wait (thread 32) run side by side; the arrival must not wait for the
+            // dependency, or two blocks could wait for each other
+            if (tid == 0 && prev_level != kNoDep) {
                 if (PROFILE) tp = clock64();
-                if (prev_level != kNoDep) red_release_gpu(a.lvl_count + prev_level);
-                if (d.dep != kNoDep) {
-                    while (ld_relaxed_gpu(a.lvl_count + d.dep) < d.dep_target) {}
-                    fence_acq_rel_gpu();
-                }
-                if (PROFILE) t_bar += clock64() - tp;
+                red_release_gpu(a.lvl_count + (size_t)prev_level * kCountStride);
+                if (PROFILE) t_rel += clock64() - tp;
             }
+            if (tid == 32 && d.dep != kNoDep) {
+                long long t0 = 0;
+                if (PROFILE) t0 = clock64();
+                const unsigned int *cnt = a.lvl_count + (size_t)d.dep * kCountStride;
+                while (ld_acquire_gpu(cnt) < d.dep_target) __nanosleep(a.poll_ns);
+                if (PROFILE) a.prof[6 * blockIdx.x + 4] += (unsigned long long)(clock64() - t0);
+            }
+            if (PROFILE && tid == 0) tp = clock64();
             __syncthreads();
+            if (PROFILE && tid == 0) t_bar += clock64() - tp;
             prev_level = d.level;
         }
         const bool epilogue = d.level >= n_real_pl;
-        double *const acc = epilogue ? acc_per : acc_cell;
+        double *const acc = epilogue ? a.acc_per + (size_t)d.group * a.n_periodic : a.acc_cell + (size_t)d.group * a.n_cells;
         const uint32_t n = d.n, E = d.n_entries;
         const TileLayout L = tile_layout(n, E);
         double *const prod = reinterpret_cast<double *>(pkt + L.w);
@@ -676,12 +691,13 @@ sweep_stream_kernel(StreamArgs a) {
         if (++stage == stages) { stage = 0; parity ^= 1u; }
     }
     __syncthreads();
-    if (tid == 0 && prev_level != kNoDep) red_release_gpu(a.lvl_count + prev_level);
+    if (tid == 0 && prev_level != kNoDep) red_release_gpu(a.lvl_count + (size_t)prev_level * kCountStride);
     if (PROFILE && tid == 0) {
-        a.prof[4 * blockIdx.x + 0] = (unsigned long long)(clock64() - t_begin);
-        a.prof[4 * blockIdx.x + 1] = (unsigned long long)t_bar;
-        a.prof[4 * blockIdx.x + 2] = (unsigned long long)t_pkt;
-        a.prof[4 * blockIdx.x + 3] = n_my;
+        a.prof[6 * blockIdx.x + 0] = (unsigned long long)(clock64() - t_begin);
+        a.prof[6 * blockIdx.x + 1] = (unsigned long long)t_bar;
+        a.prof[6 * blockIdx.x + 2] = (unsigned long long)t_pkt;
+        a.prof[6 * blockIdx.x + 3] = n_my;
+        a.prof[6 * blockIdx.x + 5] = (unsigned long long)t_rel;
     }
 }
 
@@ -740,13 +756,13 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
     unsigned long long *keys64_in = nullptr, *keys64 = nullptr, *epi_in = nullptr, *epi_sorted = nullptr, *upoff = nullptr,
                        *tentry_dev = nullptr;
     uint32_t *keys = nullptr, *cnt = nullptr, *pl_off = nullptr, *tile_cnt = nullptr, *tile_off = nullptr,
-             *tile_start = nullptr, *tab_block = nullptr;
+             *tile_start = nullptr, *tab_block = nullptr, *pl_max_dev = nullptr;
     unsigned int *counters = nullptr;   // [0] n_lag (count pass), [1] lag fill cursor, [2] error flag
     void *temp = nullptr;
     auto cleanup = [&]() {
         cudaFree(keys64_in); cudaFree(keys64); cudaFree(epi_in); cudaFree(epi_sorted); cudaFree(upoff);
         cudaFree(tentry_dev); cudaFree(keys); cudaFree(cnt); cudaFree(pl_off); cudaFree(tile_cnt); cudaFree(tile_off);
-        cudaFree(tile_start); cudaFree(tab_block); cudaFree(counters); cudaFree(temp);
+        cudaFree(tile_start); cudaFree(tab_block); cudaFree(counters); cudaFree(temp); cudaFree(pl_max_dev);
     };
     try {
         size_t bytes = 0;
@@ -817,28 +833,38 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         C.n_lag = n_lag;
         if ((uint64_t)n + n_lag >= 0x7fffff00ull) throw std::runtime_error("compile_schedule: slot index overflow");
 
-        // 5. tiles: greedy cut at segment boundaries, one warp per pseudo-level
+        // 5. tiles: greedy cut at segment boundaries, one warp per pseudo-level.  First pass: uniform
+        //    tiles of <= threads slots (sizes the ring stages and hence the grid); second pass (after 6):
+        //    per pseudo-level tile size chosen so that every block of the group gets the same number of
+        //    tiles of the level (no block idles at the level barrier because of a remainder).
         cuda_ok(cudaMalloc(&tile_cnt, sizeof(uint32_t) * (size_t)n_pl), "malloc tile_cnt");
         cuda_ok(cudaMalloc(&tile_off, sizeof(uint32_t) * ((size_t)n_pl + 1)), "malloc tile_off");
         const unsigned cut_blocks = (unsigned)(((size_t)n_pl * 32 + 127) / 128);
-        s_cut_kernel<<<cut_blocks, 128, 0, stream>>>(keys, pl_off, n_pl, n_dl, threads, nullptr, tile_cnt, nullptr);
-        std::vector<uint32_t> tcnt(n_pl), toff(n_pl + 1, 0);
-        cuda_ok(cudaMemcpyAsync(tcnt.data(), tile_cnt, sizeof(uint32_t) * n_pl, cudaMemcpyDeviceToHost, stream), "copy");
-        cuda_ok(cudaStreamSynchronize(stream), "cut sync");
-        for (uint32_t l = 0; l < n_pl; ++l) toff[l + 1] = toff[l] + tcnt[l];
-        const uint32_t n_tiles = toff[n_pl];
-        cuda_ok(cudaMemcpyAsync(tile_off, toff.data(), sizeof(uint32_t) * ((size_t)n_pl + 1), cudaMemcpyHostToDevice, stream), "copy");
-        cuda_ok(cudaMalloc(&tile_start, sizeof(uint32_t) * ((size_t)n_tiles + 1)), "malloc tile_start");
-        s_cut_kernel<<<cut_blocks, 128, 0, stream>>>(keys, pl_off, n_pl, n_dl, threads, tile_off, nullptr, tile_start);
-        std::vector<uint32_t> tstart(n_tiles + 1);
-        std::vector<unsigned long long> tentry(n_tiles + 1);
-        cuda_ok(cudaMalloc(&tentry_dev, sizeof(unsigned long long) * ((size_t)n_tiles + 1)), "malloc tentry");
-        s_gather_offsets_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, stream>>>(upoff, tile_start, n_tiles, n_all, tentry_dev);
-        cuda_ok(cudaMemcpyAsync(tstart.data(), tile_start, sizeof(uint32_t) * n_tiles, cudaMemcpyDeviceToHost, stream), "copy");
-        cuda_ok(cudaMemcpyAsync(tentry.data(), tentry_dev, sizeof(unsigned long long) * ((size_t)n_tiles + 1),
-                                cudaMemcpyDeviceToHost, stream), "copy");
-        cuda_ok(cudaStreamSynchronize(stream), "cut sync 2");
-        tstart[n_tiles] = n_all;
+        std::vector<uint32_t> tcnt(n_pl), toff(n_pl + 1, 0), tstart;
+        std::vector<unsigned long long> tentry;
+        uint32_t n_tiles = 0;
+        auto cut = [&](const uint32_t *pl_max_dev) {
+            s_cut_kernel<<<cut_blocks, 128, 0, stream>>>(keys, pl_off, n_pl, n_dl, threads, pl_max_dev, nullptr, tile_cnt, nullptr);
+            cuda_ok(cudaMemcpyAsync(tcnt.data(), tile_cnt, sizeof(uint32_t) * n_pl, cudaMemcpyDeviceToHost, stream), "copy");
+            cuda_ok(cudaStreamSynchronize(stream), "cut sync");
+            for (uint32_t l = 0; l < n_pl; ++l) toff[l + 1] = toff[l] + tcnt[l];
+            n_tiles = toff[n_pl];
+            cuda_ok(cudaMemcpyAsync(tile_off, toff.data(), sizeof(uint32_t) * ((size_t)n_pl + 1), cudaMemcpyHostToDevice, stream), "copy");
+            cudaFree(tile_start); tile_start = nullptr;
+            cudaFree(tentry_dev); tentry_dev = nullptr;
+            cuda_ok(cudaMalloc(&tile_start, sizeof(uint32_t) * ((size_t)n_tiles + 1)), "malloc tile_start");
+            s_cut_kernel<<<cut_blocks, 128, 0, stream>>>(keys, pl_off, n_pl, n_dl, threads, pl_max_dev, tile_off, nullptr, tile_start);
+            tstart.assign(n_tiles + 1, 0);
+            tentry.assign(n_tiles + 1, 0);
+            cuda_ok(cudaMalloc(&tentry_dev, sizeof(unsigned long long) * ((size_t)n_tiles + 1)), "malloc tentry");
+            s_gather_offsets_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, stream>>>(upoff, tile_start, n_tiles, n_all, tentry_dev);
+            cuda_ok(cudaMemcpyAsync(tstart.data(), tile_start, sizeof(uint32_t) * n_tiles, cudaMemcpyDeviceToHost, stream), "copy");
+            cuda_ok(cudaMemcpyAsync(tentry.data(), tentry_dev, sizeof(unsigned long long) * ((size_t)n_tiles + 1),
+                                    cudaMemcpyDeviceToHost, stream), "copy");
+            cuda_ok(cudaStreamSynchronize(stream), "cut sync 2");
+            tstart[n_tiles] = n_all;
+        };
+        cut(nullptr);
 
         // 6. launch geometry: stage size = largest packet; blocks per SM and stages from the smem budget
         uint32_t max_bytes = 0;
@@ -869,21 +895,50 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)threads, smem), "occupancy");
         if (per_sm < 1) throw std::runtime_error("compile_schedule: stream kernel does not fit on an SM");
         uint32_t nb = (uint32_t)std::min<int>(per_sm, (int)bps) * (uint32_t)num_sms;
-        nb -= nb % G;
-        if (nb < G) throw std::runtime_error("compile_schedule: fewer blocks than direction groups");
-        const uint32_t nb_g = nb / G;
+        // interleaved (default): every block serves all direction groups in turn -- group A's tiles of level l,
+        // group B's tiles of level l, group A's of level l + 1, ... -- so the latency of one group's level
+        // barrier hides behind the other groups' tiles.  Otherwise block b is dedicated to group b % G.
+        const bool interleave = env_u32("SSW_STREAM_INTERLEAVE", 1) != 0;
+        if (!interleave) {
+            nb -= nb % G;
+            if (nb < G) throw std::runtime_error("compile_schedule: fewer blocks than direction groups");
+        }
+        const uint32_t nb_g = interleave ? nb : nb / G;
         C.threads = threads;
         C.bps = bps;
         C.stages = stages;
         C.stage_bytes = stage_bytes;
         C.n_blocks = nb;
+        if (env_u32("SSW_STREAM_BALANCED", 1)) {
+            // k tiles per block and level: tile size = ceil(n_l / (nb_g k)) plus one segment of slack for
+            // the cuts at segment boundaries, so the level never needs more than nb_g * k tiles
+            std::vector<uint32_t> pl_max(n_pl);
+            for (uint32_t pl = 0; pl < n_pl; ++pl) {
+                const uint64_t n_l = pl_off_h[pl + 1] - pl_off_h[pl];
+                const uint64_t k = std::max<uint64_t>(1, (n_l + (uint64_t)nb_g * threads - 1) / ((uint64_t)nb_g * threads));
+                uint64_t sz = (n_l + nb_g * k - 1) / (nb_g * k) + n_dl;
+                sz = std::max<uint64_t>(sz, std::min<uint64_t>(threads, 2 * n_dl + 32));   // tiny levels: few tiles
+                pl_max[pl] = (uint32_t)std::min<uint64_t>(sz, threads);
+            }
+            cuda_ok(cudaMalloc(&pl_max_dev, sizeof(uint32_t) * (size_t)n_pl), "malloc pl_max");
+            cuda_ok(cudaMemcpyAsync(pl_max_dev, pl_max.data(), sizeof(uint32_t) * (size_t)n_pl, cudaMemcpyHostToDevice, stream), "copy");
+            cut(pl_max_dev);
+            bool fits = true;
+            for (uint32_t t = 0; t < n_tiles && fits; ++t) {
+                const uint32_t ns = tstart[t + 1] - tstart[t];
+                const unsigned long long E = tentry[t + 1] - tentry[t];
+                fits = ns <= threads && E <= 65535ull && tile_layout(ns, (uint32_t)E).bytes <= stage_bytes;
+            }
+            if (!fits) cut(nullptr);   // a shifted tile outgrew the ring stage: keep the uniform cut
+        }
 
         // 7. tile table (block-major), per-block streams, barrier targets and dependencies
         std::vector<uint32_t> tile_block(n_tiles), tile_level(n_tiles), per_block_count(nb, 0), rr(G, 0);
+        uint32_t rr_all = 0;
         for (uint32_t pl = 0; pl < n_pl; ++pl) {
             const uint32_t grp = pl < n_real_pl ? pl % G : pl - n_real_pl;
             for (uint32_t t = toff[pl]; t < toff[pl + 1]; ++t) {
-                const uint32_t b = grp + (rr[grp]++ % nb_g) * G;
+                const uint32_t b = interleave ? (rr_all++ % nb) : grp + (rr[grp]++ % nb_g) * G;
                 tile_block[t] = b;
                 tile_level[t] = pl;
                 per_block_count[b]++;
@@ -928,7 +983,7 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         cuda_ok(cudaMalloc(&C.stream_off, sizeof(uint64_t) * ((size_t)nb + 1)), "malloc stream_off");
         cuda_ok(cudaMalloc(&C.lvl_target, sizeof(uint32_t) * (size_t)n_pl), "malloc lvl_target");
         cuda_ok(cudaMalloc(&C.lvl_dep, sizeof(uint32_t) * (size_t)n_pl), "malloc lvl_dep");
-        cuda_ok(cudaMalloc(&C.lvl_count, sizeof(unsigned int) * (size_t)n_pl), "malloc lvl_count");
+        cuda_ok(cudaMalloc(&C.lvl_count, sizeof(unsigned int) * (size_t)n_pl * kCountStride), "malloc lvl_count");
         cuda_ok(cudaMalloc(&C.out_slot, sizeof(double) * ((size_t)n + n_lag)), "malloc out_slot");
         cuda_ok(cudaMalloc(&C.lag_src, sizeof(uint32_t) * (size_t)std::max<uint32_t>(n_lag, 1)), "malloc lag_src");
         cuda_ok(cudaMalloc(&C.acc_cell, sizeof(double) * (size_t)G * g.n_cells), "malloc acc_cell");
@@ -944,7 +999,7 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         if (n_tiles) {
             FillArgs fa;
             fa.g = g; fa.keys = keys; fa.slot_of = C.slot_of; fa.pidx = pidx; fa.upoff = upoff; fa.ttot_slot = C.ttot_slot;
-            fa.pl_off = pl_off; fa.n_pl = n_pl; fa.n_real_pl = n_real_pl; fa.n_dl = n_dl; fa.n_tasks = n;
+            fa.pl_off = pl_off; fa.n_pl = n_pl; fa.n_real_pl = n_real_pl; fa.n_dl = n_dl; fa.n_tasks = n; fa.n_groups = G;
             fa.tab = C.tab; fa.tab_block = tab_block; fa.tab_off = C.tab_off; fa.stream_off = C.stream_off;
             fa.stream = C.stream; fa.lag_src = C.lag_src; fa.lag_counter = counters + 1; fa.stages = stages;
             fa.lvl_dep = C.lvl_dep; fa.lvl_target = C.lvl_target;
@@ -1001,14 +1056,15 @@ inline void run_compiled(Compiled &C, const double2 *cellrec, double threshold, 
     a.n_cells = C.n_cells;
     a.n_periodic = C.n_periodic;
     a.solve = solve;
+    a.poll_ns = env_u32("SSW_STREAM_POLL_NS", 20);
     a.prof = nullptr;
     unsigned long long *prof_dev = nullptr;
     if (env_u32("SSW_STREAM_PROFILE", 0)) {
-        cuda_ok(cudaMalloc(&prof_dev, sizeof(unsigned long long) * 4 * (size_t)C.n_blocks), "malloc prof");
-        cuda_ok(cudaMemsetAsync(prof_dev, 0, sizeof(unsigned long long) * 4 * (size_t)C.n_blocks, stream), "memset prof");
+        cuda_ok(cudaMalloc(&prof_dev, sizeof(unsigned long long) * 6 * (size_t)C.n_blocks), "malloc prof");
+        cuda_ok(cudaMemsetAsync(prof_dev, 0, sizeof(unsigned long long) * 6 * (size_t)C.n_blocks, stream), "memset prof");
         a.prof = prof_dev;
     }
-    cuda_ok(cudaMemsetAsync(C.lvl_count, 0, sizeof(unsigned int) * (size_t)C.n_pl, stream), "memset lvl_count");
+    cuda_ok(cudaMemsetAsync(C.lvl_count, 0, sizeof(unsigned int) * (size_t)C.n_pl * kCountStride, stream), "memset lvl_count");
     cuda_ok(cudaMemsetAsync(C.acc_cell, 0, sizeof(double) * (size_t)C.n_groups * C.n_cells, stream), "memset acc_cell");
     if (C.n_periodic)
         cuda_ok(cudaMemsetAsync(C.acc_per, 0, sizeof(double) * (size_t)C.n_groups * C.n_periodic, stream), "memset acc_per");
@@ -1025,18 +1081,20 @@ inline void run_compiled(Compiled &C, const double2 *cellrec, double threshold, 
     cuda_ok(cudaLaunchCooperativeKernel((const void *)kernel, dim3(C.n_blocks), dim3(C.threads), args, smem, stream),
             "sweep_stream_kernel launch");
     if (prof_dev) {   // experiments only: where do the blocks spend their cycles?
-        std::vector<unsigned long long> h(4 * (size_t)C.n_blocks);
+        std::vector<unsigned long long> h(6 * (size_t)C.n_blocks);
         cudaMemcpyAsync(h.data(), prof_dev, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, stream);
         cudaStreamSynchronize(stream);
         cudaFree(prof_dev);
-        double tot = 0, bar = 0, pkt = 0, tiles = 0, tmax = 0;
+        double tot = 0, bar = 0, pkt = 0, tiles = 0, tmax = 0, poll = 0, rel = 0;
         for (uint32_t b = 0; b < C.n_blocks; ++b) {
-            tot += (double)h[4 * b]; bar += (double)h[4 * b + 1]; pkt += (double)h[4 * b + 2]; tiles += (double)h[4 * b + 3];
-            tmax = std::max(tmax, (double)h[4 * b]);
+            tot += (double)h[6 * b]; bar += (double)h[6 * b + 1]; pkt += (double)h[6 * b + 2]; tiles += (double)h[6 * b + 3];
+            poll += (double)h[6 * b + 4]; rel += (double)h[6 * b + 5];
+            tmax = std::max(tmax, (double)h[6 * b]);
         }
-        fprintf(stderr, "[stream profile] blocks %u tiles %.0f  cycles/block mean %.0f max %.0f  barrier %.1f%%  packet wait %.1f%%  "
-                        "cycles per tile (excl. barrier) %.0f  pseudo-levels %u\n",
-                C.n_blocks, tiles, tot / C.n_blocks, tmax, 100.0 * bar / tot, 100.0 * pkt / tot, (tot - bar) / tiles, C.n_pl);
+        fprintf(stderr, "[stream profile] blocks %u tiles %.0f  cycles/block mean %.0f max %.0f  level change: arrive %.1f%% + wait behind it %.1f%% "
+                        "(dependency poll %.1f%%)  packet wait %.1f%%  cycles per tile (excl. level changes) %.0f  pseudo-levels %u\n",
+                C.n_blocks, tiles, tot / C.n_blocks, tmax, 100.0 * rel / tot, 100.0 * bar / tot, 100.0 * poll / tot, 100.0 * pkt / tot,
+                (tot - bar - rel) / tiles, C.n_pl);
     }
     if (launch_counter) *launch_counter += launches;
 }

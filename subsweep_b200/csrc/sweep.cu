@@ -89,7 +89,10 @@ struct Schedule {
     uint32_t n_act = 0;
     uint64_t n_tasks = 0;
     uint32_t n_levels = 0;
+    uint32_t max_level_tasks = 0;
     DevBuf<uint32_t> act_list;  // ascending cell indices (empty = all cells)
+    DevBuf<uint32_t> touch_list; // Local neighbours of the active cells (photon_rate bookkeeping)
+    uint32_t n_touch = 0;
     DevBuf<uint32_t> tasks;     // level-sorted, (dl, cell)-sorted inside a level
     DevBuf<uint32_t> level_off; // n_levels + 1
     std::vector<uint32_t> level_off_host;
@@ -132,7 +135,8 @@ struct Sweep {
     DevBuf<uint8_t> flags;
     DevBuf<uint8_t> cub_temp;
     DevBuf<uint32_t> n_selected;
-    DevBuf<double> rate_act, cell_tmp, cell_tmp2;
+    DevBuf<double> rate_act, cell_tmp, cell_tmp2, photon;
+    bool photon_valid = false;  // photon = sum_d incoming[d] of this rank's directions is current
     DevBuf<double2> cellrec;
     DevBuf<unsigned long long> hist;
     DevBuf<ChemStats> chem_stats;
@@ -273,7 +277,7 @@ struct Sweep {
                 const double *temperature, const double *source);
     void refresh_histogram();
     void build_active_list(Schedule &S, int cur);
-    void gather_periodic(double *dst);
+    void gather_periodic(double *dst, const uint32_t *act, uint32_t n_act);
     void build_schedule(Schedule &S, int cur, bool solve, int dl_base, int n_dl, int32_t *wl);
     void single_sweep(int cur);
     void update_timestep_levels();
@@ -395,8 +399,8 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     att.alloc(N);
     ion_time.alloc(N);
     {
-        std::vector<double> nanv(N, std::numeric_limits<double>::quiet_NaN());
-        ion_time.upload(nanv.data(), N, stream);
+        std::vector<double> infv(N, std::numeric_limits<double>::infinity());   // IonizationTime::default(), components.rs:79-83
+        ion_time.upload(infv.data(), N, stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
     }
     pidx.alloc(N); pidx.upload(pidx_h.data(), N, stream);
@@ -415,6 +419,7 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     cellrec.alloc(N);
     cell_tmp.alloc(N);
     cell_tmp2.alloc(N);
+    photon.alloc(N); photon.zero(stream);
     hist.alloc(33);
     chem_stats.alloc(1); chem_stats.zero(stream);
     CUDA_CHECK(cudaStreamSynchronize(stream));  // host vectors go out of scope
@@ -461,12 +466,22 @@ void Sweep::build_active_list(Schedule &S, int cur) {
     CUDA_CHECK(cudaMemcpyAsync(&got, n_selected.p, sizeof got, cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
     if (got != S.n_act) fail(SSW_E_CUDA, "active list has %u cells, histogram says %u", got, S.n_act);
+    // the cells whose incoming rates a sweep over this set changes: Local neighbours of the set
+    CUDA_CHECK(cudaMemsetAsync(flags.p, 0, N, stream));
+    mark_touched_kernel<<<cdiv(S.n_act, 256), 256, 0, stream>>>(grid_view(), S.act_list.p, S.n_act, flags.p);
+    S.touch_list.ensure(N);
+    CUDA_CHECK(cub::DeviceSelect::Flagged(cub_temp.p, bytes, iota, flags.p, S.touch_list.p, n_selected.p, (int)N, stream));
+    launched(3);
+    CUDA_CHECK(cudaMemcpyAsync(&got, n_selected.p, sizeof got, cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    S.n_touch = got;
 }
 
-void Sweep::gather_periodic(double *dst) {
+void Sweep::gather_periodic(double *dst, const uint32_t *act, uint32_t n_act) {
     if (!n_periodic) return;
-    dim3 grid(cdiv(n_periodic, 256), Dl);
-    periodic_gather_kernel<<<grid, 256, 0, stream>>>(grid_view(), pcells.p, n_periodic, state_view(), dst);
+    dim3 grid(cdiv(act ? n_act : n_periodic, 256), Dl);
+    periodic_gather_kernel<<<grid, 256, 0, stream>>>(grid_view(), pcells.p, n_periodic, act, n_act, pidx.p,
+                                                     state_view(), dst);
     launched();
 }
 
@@ -494,7 +509,9 @@ void Sweep::build_schedule(Schedule &S, int cur, bool solve, int dl_base, int n_
     uint32_t *lo = level_off_scratch.p;
     uint32_t lcap = cap;
     void *args[] = {&a, &qp, &cp, &lo, &lcap, &wl};
-    CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)sweep_build_kernel, dim3(coop_blocks_build),
+    // a grid barrier costs more the more blocks take part: small active sets get a small grid
+    const unsigned build_blocks = std::max(1u, std::min<unsigned>((unsigned)coop_blocks_build, cdiv(n_tasks, 256)));
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)sweep_build_kernel, dim3(build_blocks),
                                            dim3(256), args, 0, stream));
     launched();
     QueueCtl h;
@@ -513,6 +530,9 @@ void Sweep::build_schedule(Schedule &S, int cur, bool solve, int dl_base, int n_
     CUDA_CHECK(cudaMemcpyAsync(S.level_off_host.data(), level_off_scratch.p, sizeof(uint32_t) * (h.n_levels + 1),
                                cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
+    S.max_level_tasks = 0;
+    for (uint32_t l = 0; l < h.n_levels; ++l)
+        S.max_level_tasks = std::max(S.max_level_tasks, S.level_off_host[l + 1] - S.level_off_host[l]);
 }
 
 void Sweep::maybe_allreduce(double *buf, uint64_t n) {
@@ -537,16 +557,24 @@ void Sweep::single_sweep(int cur) {
     const size_t t_sweep = tic(T_SWEEP, cur);
 
     const bool use_compiled = reuse && all && !(P.flags & SSW_FLAG_NO_COMPILED_PATH) && compiled_supported();
-    // periodic_source as the tasks of this sweep will read it (lagged, DESIGN.md section 4); the
-    // compiled path reads the donors' previous outgoing rates directly (stream.cuh)
-    if (!use_compiled) gather_periodic(per_lag.p);
-
     if (!reuse) {
-        const size_t t_sched = tic(T_SCHED);
         S.valid = false;
         if (state != &S.compiled) S.compiled.release();
         S.n_act = n_act;
-        if (!all) build_active_list(S, cur);
+        if (!all) {
+            const size_t t_list = tic(T_SCHED);
+            build_active_list(S, cur);
+            toc(t_list);
+        }
+    }
+    const uint32_t *act = all ? nullptr : S.act_list.p;
+    // periodic_source as the tasks of this sweep will read it (lagged, DESIGN.md section 4); the
+    // compiled path reads the donors' previous outgoing rates directly (stream.cuh).  A partial
+    // active set only refreshes the rows of its own cells.
+    if (!use_compiled) gather_periodic(per_lag.p, act, n_act);
+
+    if (!reuse) {
+        const size_t t_sched = tic(T_SCHED);
         const size_t t_k = tic(T_KERNEL, cur);
         build_schedule(S, cur, /*solve=*/true, 0, Dl, nullptr);
         toc(t_k);
@@ -603,7 +631,9 @@ void Sweep::single_sweep(int cur) {
             const uint32_t *lo = S.level_off.p;
             uint32_t nl = S.n_levels;
             void *args[] = {&a, &qp, &lo, &nl};
-            CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)sweep_replay_kernel, dim3(coop_blocks_replay),
+            const unsigned replay_blocks =
+                std::max(1u, std::min<unsigned>((unsigned)coop_blocks_replay, cdiv(S.max_level_tasks, 256)));
+            CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)sweep_replay_kernel, dim3(replay_blocks),
                                                    dim3(256), args, 0, stream));
             launched();
         }
@@ -620,15 +650,20 @@ void Sweep::single_sweep(int cur) {
 
     // update_chemistry (src/sweep/mod.rs:549-574)
     const size_t t_chem = tic(T_CHEM);
-    const uint32_t *act = all ? nullptr : S.act_list.p;
     if (use_compiled && S.compiled.valid) {
         // the compiled sweep left sum_d incoming and sum_d periodic_source in its group accumulators
         const Compiled &C = S.compiled;
         s_rate_finish_kernel<<<cdiv(N, 256), 256, 0, stream>>>(N, C.n_groups, n_periodic, Dl, (double)D, C.acc_cell,
-                                                               C.acc_per, pidx.p, src.p, rate_act.p, nullptr);
+                                                               C.acc_per, pidx.p, src.p, rate_act.p, photon.p);
+        photon_valid = true;
     } else {
-        gather_periodic(per_new.p);
-        launched();
+        if (all) {
+            photon_valid = false;   // re-evaluated on demand (read_field)
+        } else if (photon_valid && S.n_touch) {
+            photon_patch_kernel<<<S.n_touch, kMaxDirs, 0, stream>>>(grid_view(), state_view(), S.touch_list.p, Dl, photon.p);
+            launched();
+        }
+        gather_periodic(per_new.p, act, n_act);
         rate_kernel<<<cdiv(n_act, 256), 256, 0, stream>>>(act, n_act, N, Dl, incoming.p, pidx.p, per_new.p,
                                                           n_periodic, rate_act.p);
     }
@@ -716,6 +751,18 @@ void Sweep::read_field(int field, double *out) {
     case SSW_F_SOURCE: srcp = src.p; break;
     case SSW_F_IONIZATION_TIME: srcp = ion_time.p; break;
     case SSW_F_PHOTON_RATE:
+        if (photon_valid) {
+            // kept current by the sweeps themselves: the all-cells sweep leaves sum_d incoming in its
+            // accumulators, partial sweeps patch the cells they touch
+            if (P.world_size > 1) {
+                CUDA_CHECK(cudaMemcpyAsync(cell_tmp.p, photon.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, stream));
+                maybe_allreduce(cell_tmp.p, N);
+                srcp = cell_tmp.p;
+            } else {
+                srcp = photon.p;
+            }
+            break;
+        }
         if (state && state->valid) {
             // sum_d incoming over the compiled schedule (evaluation only, nothing is solved)
             try {

@@ -298,7 +298,7 @@ class SweepPlugin:
         n = grid.n_cells
         components.setdefault("photon_rate", np.zeros(n))
         components.setdefault("timestep", np.zeros(n))
-        components.setdefault("ionization_time", np.full(n, np.nan))
+        components.setdefault("ionization_time", np.full(n, np.inf))   # IonizationTime::default()
 
     def run_sweep_system(self, components: dict) -> None:
         # the first call is a no-op so that the initial conditions get written (mod.rs:711-714)

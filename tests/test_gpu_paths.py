@@ -55,4 +55,4 @@ def test_sweep_plugin_surface(cuda_lib):
         plugin.run_sweep_system(comps)
     ionized = comps["ionized_hydrogen_fraction"] > 0.5
     assert ionized.any()
-    assert np.all(np.isfinite(comps["ionization_time"][ionized])) and np.all(np.isnan(comps["ionization_time"][~ionized]))
+    assert np.all(np.isfinite(comps["ionization_time"][ionized])) and np.all(np.isposinf(comps["ionization_time"][~ionized]))
