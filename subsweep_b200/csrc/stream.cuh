@@ -744,8 +744,8 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
     const uint32_t n = (uint32_t)n_tasks;
     const uint32_t n_dl = (uint32_t)n_local_dirs;
     // tunables (environment overrides are for experiments; DESIGN.md section 5 lists the defaults)
-    const uint32_t threads = env_u32("SSW_STREAM_THREADS", 512) == 256 ? 256u : 512u;
-    uint32_t G = std::min<uint32_t>(env_u32("SSW_STREAM_GROUPS", 4), kMaxGroups);
+    const uint32_t threads = env_u32("SSW_STREAM_THREADS", 256) == 256 ? 256u : 512u;
+    uint32_t G = std::min<uint32_t>(env_u32("SSW_STREAM_GROUPS", 2), kMaxGroups);
     G = std::max<uint32_t>(1u, std::min<uint32_t>(G, n_dl));
     uint32_t want_bps = env_u32("SSW_STREAM_BPS", threads == 256 ? 4 : 2);
     const uint32_t want_stages = std::max<uint32_t>(1u, std::min<uint32_t>(env_u32("SSW_STREAM_STAGES", 3), kMaxStages));
