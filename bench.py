@@ -88,57 +88,96 @@ def algorithmic_bytes_per_update(g, dirs) -> tuple[float, float]:
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons of one GPU DURING the timed region: NVML in a
+    background thread every few ms (the timed region is tens of ms), nvidia-smi as fall-back."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
-    def __init__(self, device_index: int):
+    def __init__(self, device_index: int, period_s: float = 0.004):
         self.device_index = device_index
-        self.proc = None
-        self.lines: list[str] = []
+        self.period_s = period_s
+        self.samples: list[tuple[float, float, int]] = []
+        self.sm_max = None
+        self._stop = threading.Event()
         self.thread = None
+        self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = device_index
+            if visible:
+                try:
+                    index = int(visible.split(",")[device_index])
+                except (ValueError, IndexError):
+                    index = device_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        except Exception:
+            power = float("nan")
+        try:
+            reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            try:
+                reasons = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                reasons = 0
+        self.samples.append((sm, power, reasons))
+
+    def _pump(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            self._stop.wait(self.period_s)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
-                 "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+        if self.nvml is None or self.handle is None:
             return
+        self._stop.clear()
         self.thread = threading.Thread(target=self._pump, daemon=True)
         self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            self.thread = None
+        if self.nvml is None or not self.samples:
+            return self._smi_once()
+        sm = [s[0] for s in self.samples]
+        power = [s[1] for s in self.samples if s[1] == s[1]]
+        bits = 0
+        for s in self.samples:
+            bits |= s[2]
+        reasons = [name for name, bit in self.REASONS if bits & bit]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": self.sm_max, "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": reasons, "source": "nvml, sampled during the timed region"}
+
+    def _smi_once(self) -> dict:
+        query = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, power, reasons = [], [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 8:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                smax.append(float(parts[2]))
-                power.append(float(parts[3]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smax)) if smax else None,
-                "power_w_max": float(max(power)) if power else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={query}", "--format=csv,noheader,nounits", "-i",
+                                  str(self.device_index)], capture_output=True, text=True, timeout=10).stdout.strip()
+            parts = [p.strip() for p in out.split(",")]
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            reasons = [n for n, v in zip(names, parts[3:7]) if v.lower().startswith("active")]
+            return {"sm_mhz": float(parts[0]), "sm_max_mhz": float(parts[1]), "power_w_max": float(parts[2]), "samples": 1,
+                    "reasons": reasons, "source": "nvidia-smi, one sample right after the timed region (NVML unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -362,7 +401,7 @@ def run_b200(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--n", type=int, default=128, help="cells per dimension")

@@ -139,6 +139,25 @@ int ssw_read_levels(ssw_handle *h, uint8_t *out /* N */);
 int ssw_level_counts(ssw_handle *h, uint64_t *out /* n_levels, cumulative: #cells with level >= l */);
 int ssw_lowest_allowed_level(ssw_handle *h, int32_t *out);
 
+/* -- the step after the path: time series (src/sweep/time_series.rs:61-188) ------------------ */
+
+/* compute_time_series_system (time_series.rs:61-155): mass- and volume-weighted averages over all
+ * cells, reduced on the device from the resident state (no N-length read-back).  `mass` is the
+ * per-particle Mass component (host array, N) or NULL for density * volume.  The two
+ * photoionization-rate averages need the optional PhotoionizationRate output
+ * (chemistry_output.rs:25-31) and are only evaluated when with_rates != 0 (else NaN). */
+typedef struct ssw_time_series {
+    double hydrogen_ionization_mass_average;
+    double hydrogen_ionization_volume_average;
+    double temperature_mass_average;                      /* K    */
+    double temperature_volume_average;                    /* K    */
+    double photoionization_rate_volume_average;           /* 1/s  */
+    double weighted_photoionization_rate_volume_average;  /* 1/s  */
+    double total_mass, total_volume;
+} ssw_time_series;
+int ssw_time_series_compute(ssw_handle *h, const double *mass /* N or NULL */, int32_t with_rates,
+                            ssw_time_series *out);
+
 /* -- pieces, exposed for parity tests and profiling --------------------------------------- */
 
 /* Sweep::single_sweep (src/sweep/mod.rs:274-289) at `level`, including chemistry. */

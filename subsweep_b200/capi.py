@@ -68,6 +68,13 @@ class Timings(C.Structure):
         return d
 
 
+class TimeSeries(C.Structure):
+    _fields_ = [(k, C.c_double) for k in (
+        "hydrogen_ionization_mass_average", "hydrogen_ionization_volume_average", "temperature_mass_average",
+        "temperature_volume_average", "photoionization_rate_volume_average",
+        "weighted_photoionization_rate_volume_average", "total_mass", "total_volume")]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)
 
 # every symbol include/subsweep_b200.h declares: name -> (restype, argtypes)
@@ -79,6 +86,7 @@ SYMBOLS = {
     "ssw_run_sweeps": (C.c_int, [H, c_double_p]),
     "ssw_set_inputs": (C.c_int, [H, c_double_p, c_double_p]),
     "ssw_read": (C.c_int, [H, C.c_int, c_double_p]),
+    "ssw_time_series_compute": (C.c_int, [H, c_double_p, C.c_int32, C.POINTER(TimeSeries)]),
     "ssw_read_levels": (C.c_int, [H, C.POINTER(C.c_uint8)]),
     "ssw_level_counts": (C.c_int, [H, C.POINTER(C.c_uint64)]),
     "ssw_lowest_allowed_level": (C.c_int, [H, C.POINTER(C.c_int32)]),

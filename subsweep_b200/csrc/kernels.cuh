@@ -289,6 +289,19 @@ sweep_replay_kernel(SweepArgs a, const uint32_t *__restrict__ queue,
     }
 }
 
+// REPLAY of a small active set: every wavefront level fits one block, so a block-wide barrier
+// (tens of cycles) replaces the grid barrier (microseconds).  Same arithmetic as sweep_replay_kernel.
+__global__ void __launch_bounds__(1024)
+sweep_replay_small_kernel(SweepArgs a, const uint32_t *__restrict__ queue,
+                          const uint32_t *__restrict__ level_off, uint32_t n_levels) {
+    for (uint32_t lvl = 0; lvl < n_levels; ++lvl) {
+        const uint32_t s = level_off[lvl], e = level_off[lvl + 1];
+        for (uint32_t i = s + threadIdx.x; i < e; i += blockDim.x)
+            solve_task<false>(a, queue[i], nullptr, 0, nullptr, nullptr, 0, true);
+        __syncthreads();   // global writes of this level are visible to the block's next level
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // periodic_source rows: sum over LocalPeriodic upwind faces (handle_local_periodic_neighbour,
 // src/sweep/mod.rs:505-513, in gather form).  One thread per (periodic cell, local direction).
@@ -408,6 +421,29 @@ rate_kernel(const uint32_t *__restrict__ act_list, uint32_t n_act, uint32_t n_ce
         for (int dl = 0; dl < n_local_dirs; ++dl) rate += __ldcs(incoming + (size_t)dl * n_cells + c) + 0.0;
     }
     rate_act[k] = rate;
+}
+
+// the same fold for a small active set: one block per active cell, one thread per direction loads its
+// term, thread 0 folds them in direction order (bit-identical to rate_kernel, without its serial loads)
+__global__ void __launch_bounds__(kMaxDirs)
+rate_small_kernel(const uint32_t *__restrict__ act_list, uint32_t n_cells, int n_local_dirs,
+                  const double *__restrict__ incoming, const int32_t *__restrict__ pidx,
+                  const double *__restrict__ per_new, uint32_t n_periodic, double *__restrict__ rate_act) {
+    __shared__ double s_term[kMaxDirs];
+    const uint32_t k = blockIdx.x;
+    const uint32_t c = act_list[k];
+    const int dl = threadIdx.x;
+    if (dl < n_local_dirs) {
+        const int32_t p = pidx[c];
+        const double per = p >= 0 ? per_new[(size_t)dl * n_periodic + p] : 0.0;
+        s_term[dl] = __ldcs(incoming + (size_t)dl * n_cells + c) + per;
+    }
+    __syncthreads();
+    if (dl == 0) {
+        double rate = 0.0;
+        for (int d = 0; d < n_local_dirs; ++d) rate += s_term[d];
+        rate_act[k] = rate;
+    }
 }
 
 // {exp(-n_HI sigma size), source / D} per cell: the 16-byte record the compiled sweep gathers
@@ -612,6 +648,58 @@ chemistry_batch_kernel(uint64_t n, double *x, double *T, const double *rho, cons
     process[i] = r.failed ? -1 : r.process;
     depth[i] = r.max_depth;
     attempts[i] = r.attempts;
+}
+
+// ------------------------------------------------------------------------------------------
+// time series of compute_time_series_system (src/sweep/time_series.rs:61-155): mass- and
+// volume-weighted sums over all cells.  Two deterministic passes: per-block partial sums (fixed
+// tree), then one block folds the partials in block order.
+//   sums[0] = sum m x   [1] = sum m   [2] = sum V x   [3] = sum V   [4] = sum T m   [5] = sum T V
+//   [6] = sum Gamma V   [7] = sum Gamma x V        (Gamma = photoionization rate, optional)
+// ------------------------------------------------------------------------------------------
+constexpr int kSeriesSums = 8;
+
+__global__ void __launch_bounds__(256)
+time_series_partial_kernel(CellView cv, uint32_t n, const double *__restrict__ mass, const double *__restrict__ gamma,
+                           double *__restrict__ partial) {
+    __shared__ double s_red[kSeriesSums][8];
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[kSeriesSums];
+#pragma unroll
+    for (int i = 0; i < kSeriesSums; ++i) v[i] = 0.0;
+    if (c < n) {
+        const double vol = cv.volume[c], x = cv.x[c], T = cv.T[c];
+        const double m = mass ? mass[c] : cv.rho[c] * vol;
+        v[0] = m * x; v[1] = m; v[2] = vol * x; v[3] = vol; v[4] = T * m; v[5] = T * vol;
+        if (gamma) { v[6] = gamma[c] * vol; v[7] = gamma[c] * x * vol; }
+    }
+#pragma unroll
+    for (int i = 0; i < kSeriesSums; ++i) {
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_down_sync(0xffffffffu, v[i], o);
+        if ((threadIdx.x & 31) == 0) s_red[i][threadIdx.x >> 5] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < kSeriesSums) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_red[threadIdx.x][w];
+        partial[(size_t)blockIdx.x * kSeriesSums + threadIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+time_series_final_kernel(const double *__restrict__ partial, uint32_t n_blocks, double *__restrict__ sums) {
+    __shared__ double s_red[kSeriesSums][32];
+    // thread (i, j): quantity i = tid / 32, lane j folds blocks j, j + 32, ... in order
+    const int i = threadIdx.x >> 5, j = threadIdx.x & 31;
+    double t = 0.0;
+    for (uint32_t b = j; b < n_blocks; b += 32) t += partial[(size_t)b * kSeriesSums + i];
+    s_red[i][j] = t;
+    __syncthreads();
+    if (j == 0) {
+        double total = 0.0;
+        for (int k = 0; k < 32; ++k) total += s_red[i][k];
+        sums[i] = total;
+    }
 }
 
 __global__ void __launch_bounds__(256)

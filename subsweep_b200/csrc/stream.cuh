@@ -23,7 +23,7 @@
 //     order the block consumes them.  A block therefore reads one sequential byte stream, which
 //     it prefetches STAGES tiles ahead with TMA bulk copies (cp.async.bulk + mbarrier
 //     complete_tx) into a shared-memory ring, independent of the wavefront barriers.
-//   * periodic upwind faces are ordinary entries flagged kPeriodicBit.  The donor of a periodic
+//   * periodic upwind faces are ordinary entries (listed behind a slot's Local ones).  The donor of a periodic
 //     face is normally solved in a later level than its target, so reading out_slot[donor]
 //     directly yields last sweep's value: the reference's lag (src/sweep/mod.rs:505-513,
 //     site.rs:53-56).  Donors in the same or an earlier level are
@@ -59,7 +59,6 @@
 
 namespace ssw {
 
-constexpr uint32_t kPeriodicBit = 0x80000000u;
 constexpr uint32_t kNoDep = 0xffffffffu;
 constexpr int kMaxStreamThreads = 512;
 constexpr int kMaxStages = 4;
@@ -523,7 +522,6 @@ struct StreamArgs {
     double threshold;
     uint32_t stages, stage_bytes;
     uint32_t n_groups, n_real_pl, n_cells, n_periodic;
-    int solve;                // 1: sweep; 0: only accumulate sum_d incoming (photon_rate read-out)
     uint32_t poll_ns;         // back-off between polls of a level counter
     unsigned long long *prof; // optional per-block cycle counters {total, wait behind arrive, packet wait, tiles, dependency poll, arrive}
 };
@@ -551,7 +549,6 @@ sweep_stream_kernel(StreamArgs a) {
     const unsigned char *const stream = a.stream + a.stream_off[blockIdx.x];
     double *const out_slot = a.out_slot;
     const uint32_t n_real_pl = a.n_real_pl;
-    const int solve = a.solve;
     const double threshold = a.threshold;
     uint64_t policy = 0;
     if (tid == 0) {
@@ -627,10 +624,10 @@ sweep_stream_kernel(StreamArgs a) {
             const uint32_t i1 = i + THREADS, i2 = i + 2u * THREADS, i3 = i + 3u * THREADS;
             const bool p1 = i1 < E, p2 = i2 < E, p3 = i3 < E;
             double v0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-            v0 = __ldcg(out_slot + (es[i] & ~kPeriodicBit));
-            if (p1) v1 = __ldcg(out_slot + (es[i1] & ~kPeriodicBit));
-            if (p2) v2 = __ldcg(out_slot + (es[i2] & ~kPeriodicBit));
-            if (p3) v3 = __ldcg(out_slot + (es[i3] & ~kPeriodicBit));
+            v0 = __ldcg(out_slot + es[i]);
+            if (p1) v1 = __ldcg(out_slot + es[i1]);
+            if (p2) v2 = __ldcg(out_slot + es[i2]);
+            if (p3) v3 = __ldcg(out_slot + es[i3]);
             prod[i] = v0 * prod[i];
             if (p1) prod[i1] = v1 * prod[i1];
             if (p2) prod[i2] = v2 * prod[i2];
@@ -643,27 +640,30 @@ sweep_stream_kernel(StreamArgs a) {
             uint32_t e = inf & 0xffffu;
             const uint32_t em = e1 - ((inf >> 16) & 0xffu);
             double in_loc = 0.0, in_per = 0.0;
+#pragma unroll 1
             for (; e < em; ++e) in_loc += prod[e];
+#pragma unroll 1
             for (; e < e1; ++e) in_per += prod[e];
             if (epilogue) {
-                inc = solve ? in_per : 0.0;                             // periodic_source of this sweep
+                inc = in_per;                                           // periodic_source of this sweep
             } else {
                 inc = in_loc;                                           // incoming_total_rate[d]
-                if (solve) {
-                    const double total = (in_loc + rec.y) + in_per;     // site.rs:49-56
-                    // HydrogenOnly::get_outgoing_rate, hydrogen_only/mod.rs:81-87
-                    const double out = (total < threshold) ? 0.0 : total * rec.x;
-                    __stcg(out_slot + d.slot0 + tid, out);
-                }
+                const double total = (in_loc + rec.y) + in_per;         // site.rs:49-56
+                // HydrogenOnly::get_outgoing_rate, hydrogen_only/mod.rs:81-87
+                const double out = (total < threshold) ? 0.0 : total * rec.x;
+                __stcg(out_slot + d.slot0 + tid, out);
             }
         }
         // segmented suffix sums over the lanes of a warp: a lane ends up with the sum of its segment
         // from itself to the segment's end inside the warp
+        // (a lane's segment ends at the next head lane, at the first lane without a slot, or at the warp's end)
+        const uint32_t stops = __ballot_sync(0xffffffffu, (inf & kInfoHead) != 0 || tid >= n);
+        const uint32_t rest = lane == 31u ? 0u : (stops >> (lane + 1u));
+        const uint32_t seg_end = rest ? lane + (uint32_t)__ffs((int)rest) : 32u;
         double sum = inc;
         for (uint32_t st = 0, o = 1; st < d.scan_steps; ++st, o <<= 1) {
             const double v = __shfl_down_sync(0xffffffffu, sum, o);
-            const uint32_t cc = __shfl_down_sync(0xffffffffu, c, o);
-            if (lane + o < 32u && cc == c) sum += v;
+            if (lane + o < seg_end) sum += v;
         }
         const uint32_t c_last = __shfl_sync(0xffffffffu, c, 31);
         const uint32_t buf = k & 1u;
@@ -686,7 +686,7 @@ sweep_stream_kernel(StreamArgs a) {
                     if (s_wlast[buf][ww] != c) break;
                 }
             }
-            if (solve || !epilogue) __stcg(acc + c, acc_old + sum);
+            __stcg(acc + c, acc_old + sum);
         }
         if (++stage == stages) { stage = 0; parity ^= 1u; }
     }
@@ -1032,9 +1032,8 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
     C.valid = true;
 }
 
-// One all-cells sweep (solve = 1) or one evaluation of sum_d incoming (solve = 0) over the compiled
-// schedule.  Leaves the per-group sums in C.acc_cell / C.acc_per (s_rate_finish_kernel folds them).
-inline void run_compiled(Compiled &C, const double2 *cellrec, double threshold, int solve, cudaStream_t stream,
+// One all-cells sweep over the compiled schedule.  Leaves the per-group sums in C.acc_cell / C.acc_per (s_rate_finish_kernel folds them).
+inline void run_compiled(Compiled &C, const double2 *cellrec, double threshold, cudaStream_t stream,
                          uint64_t *launch_counter) {
     StreamArgs a;
     a.stream = C.stream;
@@ -1055,7 +1054,6 @@ inline void run_compiled(Compiled &C, const double2 *cellrec, double threshold, 
     a.n_real_pl = C.n_levels * C.n_groups;
     a.n_cells = C.n_cells;
     a.n_periodic = C.n_periodic;
-    a.solve = solve;
     a.poll_ns = env_u32("SSW_STREAM_POLL_NS", 20);
     a.prof = nullptr;
     unsigned long long *prof_dev = nullptr;
@@ -1069,7 +1067,7 @@ inline void run_compiled(Compiled &C, const double2 *cellrec, double threshold, 
     if (C.n_periodic)
         cuda_ok(cudaMemsetAsync(C.acc_per, 0, sizeof(double) * (size_t)C.n_groups * C.n_periodic, stream), "memset acc_per");
     uint64_t launches = 1;
-    if (solve && C.n_lag) {
+    if (C.n_lag) {
         s_lag_snapshot_kernel<<<(C.n_lag + 255) / 256, 256, 0, stream>>>(C.lag_src, C.n_lag, (uint32_t)C.n_tasks, C.out_slot);
         ++launches;
     }

@@ -621,7 +621,7 @@ void Sweep::single_sweep(int cur) {
             try {
                 cellrec_kernel<<<cdiv(N, 256), 256, 0, stream>>>(att.p, src.p, (double)D, N, cellrec.p);
                 launched();
-                run_compiled(S.compiled, cellrec.p, P.significant_rate_threshold_per_s, /*solve=*/1, stream,
+                run_compiled(S.compiled, cellrec.p, P.significant_rate_threshold_per_s, stream,
                              &stat[SSW_STAT_KERNEL_LAUNCHES]);
             } catch (const std::exception &e) {
                 fail(SSW_E_CUDA, "%s", e.what());
@@ -631,10 +631,15 @@ void Sweep::single_sweep(int cur) {
             const uint32_t *lo = S.level_off.p;
             uint32_t nl = S.n_levels;
             void *args[] = {&a, &qp, &lo, &nl};
-            const unsigned replay_blocks =
-                std::max(1u, std::min<unsigned>((unsigned)coop_blocks_replay, cdiv(S.max_level_tasks, 256)));
-            CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)sweep_replay_kernel, dim3(replay_blocks),
-                                                   dim3(256), args, 0, stream));
+            if (S.max_level_tasks <= 2048) {
+                // every level fits one block: block barrier instead of the grid barrier
+                sweep_replay_small_kernel<<<1, 1024, 0, stream>>>(a, qp, lo, nl);
+            } else {
+                const unsigned replay_blocks =
+                    std::max(1u, std::min<unsigned>((unsigned)coop_blocks_replay, cdiv(S.max_level_tasks, 256)));
+                CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)sweep_replay_kernel, dim3(replay_blocks),
+                                                       dim3(256), args, 0, stream));
+            }
             launched();
         }
         toc(t_k);
@@ -664,8 +669,11 @@ void Sweep::single_sweep(int cur) {
             launched();
         }
         gather_periodic(per_new.p, act, n_act);
-        rate_kernel<<<cdiv(n_act, 256), 256, 0, stream>>>(act, n_act, N, Dl, incoming.p, pidx.p, per_new.p,
-                                                          n_periodic, rate_act.p);
+        if (act && n_act <= 4096)
+            rate_small_kernel<<<n_act, kMaxDirs, 0, stream>>>(act, N, Dl, incoming.p, pidx.p, per_new.p, n_periodic, rate_act.p);
+        else
+            rate_kernel<<<cdiv(n_act, 256), 256, 0, stream>>>(act, n_act, N, Dl, incoming.p, pidx.p, per_new.p,
+                                                              n_periodic, rate_act.p);
     }
     launched();
     maybe_allreduce(rate_act.p, n_act);
@@ -763,20 +771,7 @@ void Sweep::read_field(int field, double *out) {
             }
             break;
         }
-        if (state && state->valid) {
-            // sum_d incoming over the compiled schedule (evaluation only, nothing is solved)
-            try {
-                run_compiled(*state, cellrec.p, P.significant_rate_threshold_per_s, /*solve=*/0, stream,
-                             &stat[SSW_STAT_KERNEL_LAUNCHES]);
-            } catch (const std::exception &e) {
-                fail(SSW_E_CUDA, "%s", e.what());
-            }
-            s_rate_finish_kernel<<<cdiv(N, 256), 256, 0, stream>>>(N, state->n_groups, n_periodic, Dl, (double)D,
-                                                                   state->acc_cell, state->acc_per, pidx.p, src.p,
-                                                                   nullptr, cell_tmp.p);
-        } else {
-            dir_state_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), state_view(), 0, Dl, nullptr, cell_tmp.p);
-        }
+        dir_state_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), state_view(), 0, Dl, nullptr, cell_tmp.p);
         launched();
         maybe_allreduce(cell_tmp.p, N);
         srcp = cell_tmp.p;
@@ -887,6 +882,45 @@ int ssw_read(ssw_handle *h, ssw_field field, double *out) {
     if (!out) ssw::fail(SSW_E_INVALID, "null out pointer");
     h->s.read_field((int)field, out);
     h->s.resolve_timers();
+    SSW_CATCH
+}
+
+int ssw_time_series_compute(ssw_handle *h, const double *mass, int32_t with_rates, ssw_time_series *out) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    if (!out) ssw::fail(SSW_E_INVALID, "null out pointer");
+    auto &s = h->s;
+    s.bind();
+    const uint32_t nb = ssw::cdiv(s.N, 256);
+    ssw::DevBuf<double> partial, sums, mass_dev;
+    partial.alloc((size_t)nb * ssw::kSeriesSums);
+    sums.alloc(ssw::kSeriesSums);
+    if (mass) { mass_dev.alloc(s.N); mass_dev.upload(mass, s.N, s.stream); }
+    const double *gamma = nullptr;
+    if (with_rates) {   // PhotoionizationRate of every cell, as sweep_optional_output_system computes it
+        s.all_rates(s.rate_act.p);
+        ssw::chem_output_kernel<<<nb, 256, 0, s.stream>>>(s.cell_view(), s.N, s.rate_act.p, s.P.scale_factor,
+                                                         SSW_F_PHOTOIONIZATION_RATE, s.cell_tmp.p);
+        s.launched();
+        gamma = s.cell_tmp.p;
+    }
+    ssw::time_series_partial_kernel<<<nb, 256, 0, s.stream>>>(s.cell_view(), s.N, mass ? mass_dev.p : nullptr, gamma, partial.p);
+    ssw::time_series_final_kernel<<<1, 256, 0, s.stream>>>(partial.p, nb, sums.p);
+    s.launched(2);
+    CUDA_CHECK(cudaGetLastError());
+    double v[ssw::kSeriesSums];
+    CUDA_CHECK(cudaMemcpyAsync(v, sums.p, sizeof v, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    out->hydrogen_ionization_mass_average = v[0] / v[1];      // time_series.rs:81-83
+    out->hydrogen_ionization_volume_average = v[2] / v[3];    // :91-97
+    out->temperature_mass_average = v[4] / v[1];              // :106-112
+    out->temperature_volume_average = v[5] / v[3];            // :120-125
+    out->photoionization_rate_volume_average = with_rates ? v[6] / v[3] : nan;            // :134-139
+    out->weighted_photoionization_rate_volume_average = with_rates ? v[7] / v[3] : nan;   // :148-153
+    out->total_mass = v[1];
+    out->total_volume = v[3];
+    s.resolve_timers();
     SSW_CATCH
 }
 

@@ -222,6 +222,21 @@ class Sweep:
         self._check(self.lib.ssw_read(self._h, capi.FIELDS[field_name], capi.dptr(out)))
         return out
 
+    def time_series(self, mass=None, with_rates: bool = False) -> dict:
+        """compute_time_series_system (src/sweep/time_series.rs:61-155), reduced on the device; keys are the
+        reference's time-series names."""
+        ts = capi.TimeSeries()
+        m = None if mass is None else np.ascontiguousarray(mass, dtype=np.float64)
+        self._check(self.lib.ssw_time_series_compute(self._h, capi.dptr(m) if m is not None else None,
+                                                     int(with_rates), C.byref(ts)))
+        return {k: getattr(ts, k) for k, _ in capi.TimeSeries._fields_}
+
+    def num_particles_at_timestep_levels(self) -> list:
+        """num_particles_at_timestep_levels_system (time_series.rs:167-188): cumulative counts per level."""
+        counts = self.level_counts()
+        return [{"level": l, "num": int(counts[l]), "timestep": self.parameters.max_timestep * 0.5 ** l}
+                for l in range(self.parameters.num_timestep_levels)]
+
     def levels(self) -> np.ndarray:
         out = np.empty(self.n_cells, dtype=np.uint8)
         self._check(self.lib.ssw_read_levels(self._h, out.ctypes.data_as(C.POINTER(C.c_uint8))))

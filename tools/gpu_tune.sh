@@ -1,5 +1,5 @@
 #!/bin/bash
-# tuning sweep of the stream kernel: lines of "threads blocks_per_sm groups stages balanced interleave"
+# tuning sweep of the stream kernel: lines of "threads blocks_per_sm groups stages [balanced] [interleave] [poll_ns]"
 set -u
 OUT=gpurun_out; mkdir -p $OUT
 : > $OUT/tune.jsonl
