@@ -105,10 +105,11 @@ typedef enum ssw_field {
 } ssw_field;
 
 /* all-reduce hook for direction sharding: sum `n` doubles in place over all ranks.  `buf` is a
- * DEVICE pointer on params.device_id; `cuda_stream` is the cudaStream_t the library works on
- * (work queued before the call is complete when the hook is entered; the hook must leave the
- * result complete or ordered on that stream).  Replaces the MPI flux messages of
- * src/sweep/communicator.rs:59-95. */
+ * DEVICE pointer on params.device_id; `cuda_stream` is the cudaStream_t the library works on.
+ * The call is stream-ordered: the values in `buf` are produced by work already queued on that
+ * stream, and the hook must leave the reduced result ordered on the same stream (e.g.
+ * ncclAllReduce(buf, buf, n, ncclDouble, ncclSum, comm, cuda_stream)); no host synchronisation
+ * on either side.  Replaces the MPI flux messages of src/sweep/communicator.rs:59-95. */
 typedef int (*ssw_allreduce_fn)(void *ctx, double *buf, uint64_t n, void *cuda_stream);
 
 /* -- life cycle ------------------------------------------------------------------------- */

@@ -180,16 +180,32 @@ __device__ __forceinline__ void solve_task(const SweepArgs &a, uint32_t task, ui
     }
     if (valid && a.solve) {
         double in = 0.0, ttot = 0.0;
-        for (uint32_t f = f0; f < f1; ++f) {
-            const double4 geo = ld_geo(a.g.face_geo + f);
-            const double d = dot_dir(geo, dx, dy, dz);
-            if (d < 0.0) {
-                if (a.g.face_kind[f] == 0) {
-                    const double w = __ldg(a.g.face_rev + f) * (-d);
-                    in += a.st.load_q(dl, (uint32_t)a.g.face_nb[f]) * w;
+        // faces in chunks of kChunk: all loads of a chunk are issued before the first use, so a task costs a few
+        // dependent memory round trips instead of a few per face; the sums still run in face order
+        constexpr int kChunk = 8;
+        for (uint32_t fb = f0; fb < f1; fb += kChunk) {
+            double dd[kChunk], area[kChunk], w[kChunk], qv[kChunk];
+            uint32_t nb[kChunk];
+            bool up[kChunk];
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                const uint32_t f = fb + j;
+                dd[j] = 0.0; area[j] = 0.0; w[j] = 0.0; nb[j] = 0; up[j] = false;
+                if (f < f1) {
+                    const double4 geo = ld_geo(a.g.face_geo + f);
+                    dd[j] = dot_dir(geo, dx, dy, dz);
+                    area[j] = geo.w;
+                    up[j] = dd[j] < 0.0 && a.g.face_kind[f] == 0;
+                    nb[j] = (uint32_t)a.g.face_nb[f];
+                    w[j] = __ldg(a.g.face_rev + f);
                 }
-            } else if (d > 0.0) {
-                ttot += geo.w * d;
+            }
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) qv[j] = up[j] ? a.st.load_q(dl, nb[j]) : 0.0;
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                if (up[j]) in += qv[j] * (w[j] * (-dd[j]));
+                else if (dd[j] > 0.0) ttot += area[j] * dd[j];
             }
         }
         const double inc = in + a.src[c] / a.n_dirs_total;           // site.rs:49-56
@@ -291,7 +307,7 @@ sweep_replay_kernel(SweepArgs a, const uint32_t *__restrict__ queue,
 
 // REPLAY of a small active set: every wavefront level fits one block, so a block-wide barrier
 // (tens of cycles) replaces the grid barrier (microseconds).  Same arithmetic as sweep_replay_kernel.
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 sweep_replay_small_kernel(SweepArgs a, const uint32_t *__restrict__ queue,
                           const uint32_t *__restrict__ level_off, uint32_t n_levels) {
     for (uint32_t lvl = 0; lvl < n_levels; ++lvl) {
@@ -299,6 +315,132 @@ sweep_replay_small_kernel(SweepArgs a, const uint32_t *__restrict__ queue,
         for (uint32_t i = s + threadIdx.x; i < e; i += blockDim.x)
             solve_task<false>(a, queue[i], nullptr, 0, nullptr, nullptr, 0, true);
         __syncthreads();   // global writes of this level are visible to the block's next level
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Task records of a cached partial schedule ("mini" form): what solve_task derives from the CSR grid
+// on every replay -- own state index, sum_downwind(A n.d), and per Local upwind face the neighbour's
+// state index and weight -- is stored once per task in level order, so a replay costs three
+// dependent memory round trips per wavefront level instead of one or two per face.
+//   natural state (q = out / ttot, [dl][c]):  src = dl*N + nb,  w = A_rev (-n.d)        (same arithmetic as solve_task)
+//   slot-ordered state (out_slot, stream.cuh): src = slot(nb),   w = A_rev (-n.d) / ttot(nb)
+// ------------------------------------------------------------------------------------------
+struct MiniView {
+    const uint32_t *off;    // n_tasks + 1
+    const uint32_t *src;    // entries
+    const double *w;        // entries
+    const uint32_t *self;   // n_tasks: own state index
+    const double *ttot;     // n_tasks
+};
+
+__global__ void __launch_bounds__(256)
+mini_count_kernel(GridView g, const uint32_t *__restrict__ tasks, uint32_t n_tasks, uint32_t *__restrict__ cnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tasks) return;
+    const uint32_t t = tasks[i];
+    const uint32_t dl = t / g.n_cells, c = t - dl * g.n_cells;
+    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    uint32_t m = 0;
+    for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f)
+        if (g.face_kind[f] == 0 && dot_dir(ld_geo(g.face_geo + f), dx, dy, dz) < 0.0) ++m;
+    cnt[i] = m;
+}
+
+__global__ void __launch_bounds__(256)
+mini_fill_kernel(GridView g, StateView st, const uint32_t *__restrict__ tasks, uint32_t n_tasks,
+                 const uint32_t *__restrict__ off, uint32_t *__restrict__ src, double *__restrict__ w,
+                 uint32_t *__restrict__ self, double *__restrict__ ttot_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tasks) return;
+    const uint32_t t = tasks[i];
+    const uint32_t N = g.n_cells;
+    const uint32_t dl = t / N, c = t - dl * N;
+    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    uint32_t e = off[i];
+    double ttot = 0.0;
+    for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
+        const double4 geo = ld_geo(g.face_geo + f);
+        const double d = dot_dir(geo, dx, dy, dz);
+        if (d < 0.0) {
+            if (g.face_kind[f] == 0) {
+                const uint32_t nb = (uint32_t)g.face_nb[f];
+                const double wf = __ldg(g.face_rev + f) * (-d);
+                if (st.slot_of) {
+                    const uint32_t sl = st.slot_of[(size_t)dl * N + nb];
+                    const double tt = st.ttot_slot[sl];
+                    src[e] = sl;
+                    w[e] = tt > 0.0 ? wf / tt : 0.0;
+                } else {
+                    src[e] = dl * N + nb;
+                    w[e] = wf;
+                }
+                ++e;
+            }
+        } else if (d > 0.0) {
+            ttot += geo.w * d;
+        }
+    }
+    self[i] = st.slot_of ? st.slot_of[(size_t)dl * N + c] : t;
+    ttot_out[i] = ttot;
+}
+
+__device__ __forceinline__ void mini_task(const SweepArgs &a, const MiniView &m, uint32_t i, uint32_t task) {
+    const uint32_t N = a.g.n_cells;
+    const uint32_t dl = task / N, c = task - dl * N;
+    const uint32_t e0 = m.off[i], e1 = m.off[i + 1];
+    const double *state = a.st.slot_of ? a.st.out_slot : a.st.q;
+    double in = 0.0;
+    constexpr int kChunk = 8;
+    for (uint32_t eb = e0; eb < e1; eb += kChunk) {
+        uint32_t sidx[kChunk];
+        double wv[kChunk], v[kChunk];
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) {
+            const bool ok = eb + j < e1;
+            sidx[j] = ok ? m.src[eb + j] : 0u;
+            wv[j] = ok ? m.w[eb + j] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) v[j] = eb + j < e1 ? __ldcg(state + sidx[j]) : 0.0;
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j)
+            if (eb + j < e1) in += v[j] * wv[j];
+    }
+    const double inc = in + a.src[c] / a.n_dirs_total;           // site.rs:49-56
+    const int32_t p = a.pidx[c];
+    const double total = p >= 0 ? inc + a.per_lag[(size_t)dl * a.n_periodic + p] : inc + 0.0;
+    const double out = (total < a.threshold) ? 0.0 : total * a.att[c];
+    if (a.st.slot_of) {
+        __stcg(a.st.out_slot + m.self[i], out);
+    } else {
+        const double ttot = m.ttot[i];
+        __stcg(a.st.q + m.self[i], ttot > 0.0 ? out / ttot : 0.0);
+    }
+    __stcg(a.incoming + (size_t)dl * N + c, inc);
+}
+
+// every wavefront level fits one block: block barrier between levels
+__global__ void __launch_bounds__(512)
+mini_replay_small_kernel(SweepArgs a, MiniView m, const uint32_t *__restrict__ queue,
+                         const uint32_t *__restrict__ level_off, uint32_t n_levels) {
+    for (uint32_t lvl = 0; lvl < n_levels; ++lvl) {
+        const uint32_t s = level_off[lvl], e = level_off[lvl + 1];
+        for (uint32_t i = s + threadIdx.x; i < e; i += blockDim.x) mini_task(a, m, i, queue[i]);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mini_replay_kernel(SweepArgs a, MiniView m, const uint32_t *__restrict__ queue,
+                   const uint32_t *__restrict__ level_off, uint32_t n_levels) {
+    cg::grid_group grid = cg::this_grid();
+    const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int gsz = gridDim.x * blockDim.x;
+    for (uint32_t lvl = 0; lvl < n_levels; ++lvl) {
+        const uint32_t s = level_off[lvl], e = level_off[lvl + 1];
+        for (uint32_t i = s + gtid; i < e; i += gsz) mini_task(a, m, i, queue[i]);
+        if (lvl + 1 < n_levels) grid.sync();
     }
 }
 
@@ -385,10 +527,28 @@ photon_patch_kernel(GridView g, StateView st, const uint32_t *__restrict__ touch
     if (dl < n_local_dirs) {
         const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
         double acc = 0.0;
-        for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
-            if (g.face_kind[f] != 0) continue;
-            const double d = dot_dir(ld_geo(g.face_geo + f), dx, dy, dz);
-            if (d < 0.0) acc += st.load_q(dl, (uint32_t)g.face_nb[f]) * (__ldg(g.face_rev + f) * (-d));
+        constexpr int kChunk = 8;
+        const uint32_t f0 = g.face_off[c], f1 = g.face_off[c + 1];
+        for (uint32_t fb = f0; fb < f1; fb += kChunk) {
+            double wd[kChunk], qv[kChunk];
+            uint32_t nb[kChunk];
+            bool up[kChunk];
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                const uint32_t f = fb + j;
+                wd[j] = 0.0; nb[j] = 0; up[j] = false;
+                if (f < f1) {
+                    const double d = dot_dir(ld_geo(g.face_geo + f), dx, dy, dz);
+                    up[j] = d < 0.0 && g.face_kind[f] == 0;
+                    nb[j] = (uint32_t)g.face_nb[f];
+                    wd[j] = __ldg(g.face_rev + f) * (-d);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) qv[j] = up[j] ? st.load_q(dl, nb[j]) : 0.0;
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j)
+                if (up[j]) acc += qv[j] * wd[j];
         }
         s_in[dl] = acc;
     }

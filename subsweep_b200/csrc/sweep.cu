@@ -96,7 +96,13 @@ struct Schedule {
     DevBuf<uint32_t> tasks;     // level-sorted, (dl, cell)-sorted inside a level
     DevBuf<uint32_t> level_off; // n_levels + 1
     std::vector<uint32_t> level_off_host;
-    Compiled compiled;          // slot-ordered form (compiled.cuh), optional
+    Compiled compiled;          // slot-ordered form (stream.cuh), all-cells sweep only
+    // task records of a cached partial schedule (kernels.cuh, MiniView)
+    bool mini_valid = false;
+    bool mini_slot_state = false;   // built against the slot-ordered flux state
+    DevBuf<uint32_t> m_off, m_src, m_self;
+    DevBuf<double> m_w, m_ttot;
+    MiniView mini_view() const { return MiniView{m_off.p, m_src.p, m_w.p, m_self.p, m_ttot.p}; }
 };
 
 enum TimerCat { T_SWEEP = 0, T_CHEM, T_LEVELS, T_SCHED, T_ALLREDUCE, T_KERNEL, T_STEP, T_COUNT };
@@ -161,7 +167,7 @@ struct Sweep {
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> event_pool;
     ssw_timings timings{};
-    int coop_blocks_build = 0, coop_blocks_replay = 0;
+    int coop_blocks_build = 0, coop_blocks_replay = 0, coop_blocks_mini = 0;
 
     ~Sweep() {
         for (auto &p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -279,6 +285,7 @@ struct Sweep {
     void build_active_list(Schedule &S, int cur);
     void gather_periodic(double *dst, const uint32_t *act, uint32_t n_act);
     void build_schedule(Schedule &S, int cur, bool solve, int dl_base, int n_dl, int32_t *wl);
+    void build_mini(Schedule &S);
     void single_sweep(int cur);
     void update_timestep_levels();
     double run_sweeps();
@@ -437,6 +444,7 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     for (auto &s : sched) s.reset(new Schedule());
     coop_blocks_build = coop_grid((const void *)sweep_build_kernel, 256, num_sms);
     coop_blocks_replay = coop_grid((const void *)sweep_replay_kernel, 256, num_sms);
+    coop_blocks_mini = coop_grid((const void *)mini_replay_kernel, 256, num_sms);
     CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
@@ -535,11 +543,40 @@ void Sweep::build_schedule(Schedule &S, int cur, bool solve, int dl_base, int n_
         S.max_level_tasks = std::max(S.max_level_tasks, S.level_off_host[l + 1] - S.level_off_host[l]);
 }
 
+// task records for replays of a cached partial schedule (kernels.cuh, MiniView)
+void Sweep::build_mini(Schedule &S) {
+    const uint32_t n = (uint32_t)S.n_tasks;
+    S.mini_valid = false;
+    if (n == 0) return;
+    S.m_off.ensure((size_t)n + 1);
+    CUDA_CHECK(cudaMemsetAsync(S.m_off.p + n, 0, sizeof(uint32_t), stream));
+    queue_scratch.ensure((size_t)n + 1);   // entry counts (the level-sorted tasks live in S.tasks by now)
+    CUDA_CHECK(cudaMemsetAsync(queue_scratch.p + n, 0, sizeof(uint32_t), stream));
+    mini_count_kernel<<<cdiv(n, 256), 256, 0, stream>>>(grid_view(), S.tasks.p, n, queue_scratch.p);
+    size_t bytes = 0;
+    CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, queue_scratch.p, S.m_off.p, (int)n + 1, stream));
+    cub_temp.ensure(bytes);
+    CUDA_CHECK(cub::DeviceScan::ExclusiveSum(cub_temp.p, bytes, queue_scratch.p, S.m_off.p, (int)n + 1, stream));
+    uint32_t n_entries = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n_entries, S.m_off.p + n, sizeof n_entries, cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    S.m_src.ensure(n_entries);
+    S.m_w.ensure(n_entries);
+    S.m_self.ensure(n);
+    S.m_ttot.ensure(n);
+    mini_fill_kernel<<<cdiv(n, 256), 256, 0, stream>>>(grid_view(), state_view(), S.tasks.p, n, S.m_off.p, S.m_src.p, S.m_w.p,
+                                                       S.m_self.p, S.m_ttot.p);
+    launched(4);
+    CUDA_CHECK(cudaGetLastError());
+    S.mini_valid = true;
+    S.mini_slot_state = state != nullptr;
+}
+
 void Sweep::maybe_allreduce(double *buf, uint64_t n) {
     if (P.world_size <= 1) return;  // one direction shard: no collective (north_star)
     if (!allreduce) fail(SSW_E_COMM, "world_size > 1 but no all-reduce hook set (ssw_set_allreduce)");
     const size_t t = tic(T_ALLREDUCE);
-    CUDA_CHECK(cudaStreamSynchronize(stream));
+    // stream-ordered: the hook enqueues the collective behind the work already queued on `stream`
     if (allreduce(allreduce_ctx, buf, n, (void *)stream) != 0) fail(SSW_E_COMM, "all-reduce hook failed");
     toc(t);
 }
@@ -559,6 +596,7 @@ void Sweep::single_sweep(int cur) {
     const bool use_compiled = reuse && all && !(P.flags & SSW_FLAG_NO_COMPILED_PATH) && compiled_supported();
     if (!reuse) {
         S.valid = false;
+        S.mini_valid = false;
         if (state != &S.compiled) S.compiled.release();
         S.n_act = n_act;
         if (!all) {
@@ -631,9 +669,22 @@ void Sweep::single_sweep(int cur) {
             const uint32_t *lo = S.level_off.p;
             uint32_t nl = S.n_levels;
             void *args[] = {&a, &qp, &lo, &nl};
-            if (S.max_level_tasks <= 2048) {
+            // partial schedules replay from stored task records; they are (re)built on first use and when the
+            // flux state moved into slot order since
+            const bool want_mini = !all && S.n_tasks <= (64u << 20);
+            if (want_mini && (!S.mini_valid || S.mini_slot_state != (state != nullptr))) build_mini(S);
+            if (want_mini && S.mini_valid) {
+                MiniView mv = S.mini_view();
+                if (S.max_level_tasks <= 2048) {
+                    mini_replay_small_kernel<<<1, 512, 0, stream>>>(a, mv, qp, lo, nl);
+                } else {
+                    void *margs[] = {&a, &mv, &qp, &lo, &nl};
+                    const unsigned blocks = std::max(1u, std::min<unsigned>((unsigned)coop_blocks_mini, cdiv(S.max_level_tasks, 256)));
+                    CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)mini_replay_kernel, dim3(blocks), dim3(256), margs, 0, stream));
+                }
+            } else if (S.max_level_tasks <= 2048) {
                 // every level fits one block: block barrier instead of the grid barrier
-                sweep_replay_small_kernel<<<1, 1024, 0, stream>>>(a, qp, lo, nl);
+                sweep_replay_small_kernel<<<1, 512, 0, stream>>>(a, qp, lo, nl);
             } else {
                 const unsigned replay_blocks =
                     std::max(1u, std::min<unsigned>((unsigned)coop_blocks_replay, cdiv(S.max_level_tasks, 256)));

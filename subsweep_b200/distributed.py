@@ -39,10 +39,11 @@ def make_allreduce(device, group=None):
     def allreduce(ptr: int, n: int, stream) -> None:
         t = tensor_from_pointer(ptr, n, device)
         if device.type == "cuda":
-            # the library has synchronised its stream before calling the hook
-            with torch.cuda.device(device):
+            # stream-ordered on the library's own stream: torch's NCCL stream waits for the work queued
+            # there and the stream waits for the collective; no host synchronisation
+            ext = torch.cuda.ExternalStream(stream, device=device) if stream else torch.cuda.current_stream(device)
+            with torch.cuda.device(device), torch.cuda.stream(ext):
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-                torch.cuda.current_stream(device).synchronize()
         else:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
