@@ -37,11 +37,35 @@ UNIT = "updates/s"
 # ---------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------
-def build_workload(n: int, grid_kind: str, n_dirs: int, n_levels: int):
+def build_front_workload(n: int, n_dirs: int, n_levels: int):
+    """chemistry-stiff ionization front.  n^3 Cartesian box, non-periodic,
+    dense neutral slab x in [0.25, 0.75] (n_H = 1 cm^-3, elsewhere 1e-4), one 5e54 /s source at the centre of
+    the -x face."""
+    from subsweep_b200 import SweepParameters, grid as G
+    from subsweep_b200 import units as U
+
+    cell = 10.0 * U.MEGAPARSEC / 128.0
+    g = G.cartesian((n, n, n), cell * n, periodic=False)
+    ix = np.arange(g.n_cells) // (n * n)
+    slab = (ix >= n // 4) & (ix < 3 * n // 4)
+    rho = np.where(slab, 1.0, 1e-4) * U.PER_CUBIC_CENTIMETER * U.PROTON_MASS
+    src = np.zeros(g.n_cells)
+    src[(0 * n + n // 2) * n + n // 2] = 5e54
+    fields = dict(density=rho, ionized_hydrogen_fraction=np.full(g.n_cells, 1e-10), temperature=np.full(g.n_cells, 100.0),
+                  source=src)
+    params = SweepParameters(directions=n_dirs, num_timestep_levels=n_levels, periodic=False,
+                             max_timestep=1.0 * U.MEGAYEARS, significant_rate_threshold=1e-5,
+                             timestep_safety_factor=0.1, chemistry_timestep_safety_factor=0.1, prevent_cooling=True)
+    return params, g, fields
+
+
+def build_workload(n: int, grid_kind: str, n_dirs: int, n_levels: int, workload: str = "box"):
     """SURVEY.md section 8d config 2 at n^3 cells (cell size fixed at 10 Mpc / 128)."""
     from subsweep_b200 import SweepParameters, grid as G
     from subsweep_b200 import units as U
 
+    if workload == "front":
+        return build_front_workload(n, n_dirs, n_levels)
     cell = 10.0 * U.MEGAPARSEC / 128.0
     box = cell * n
     if grid_kind == "cartesian":
@@ -183,11 +207,11 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arms (the oracle; the only place bench.py touches oracle/)
 # ---------------------------------------------------------------------------------------------
-def cpu_run(n: int, grid_kind: str, n_dirs: int, n_levels: int, steps: int, warmup: int, threads: int):
+def cpu_run(n: int, grid_kind: str, n_dirs: int, n_levels: int, steps: int, warmup: int, threads: int, workload: str = "box"):
     """The CPU restatement of the reference algorithm (oracle/, kind "port") on a bounded sample
     of the workload: the same box at n^3 cells.  Returns (updates/s, ms per step, sample text)."""
     import oracle
-    params, g, f = build_workload(n, grid_kind, n_dirs, n_levels)
+    params, g, f = build_workload(n, grid_kind, n_dirs, n_levels, workload)
     s = oracle.OracleSweep(params, g, **f, periodic_mode=oracle.PERIODIC_LAGGED)
     for _ in range(n_levels):          # spin-up: unlock all timestep levels (same as the GPU arm)
         s.run_sweeps_threads(threads)
@@ -216,7 +240,7 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     threads = host_threads()
-    value, ms, sample, _ = cpu_run(args.cpu_n, args.grid, args.dirs, args.levels, args.steps, args.warmup, threads)
+    value, ms, sample, _ = cpu_run(args.cpu_n, args.grid, args.dirs, args.levels, args.steps, args.warmup, threads, args.workload)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -230,10 +254,15 @@ def run_reference(args) -> None:
 
 
 def workload_config(args, note: str | None = None) -> dict:
+    if args.workload == "front":
+        text = (f"{args.n}^3-cell Cartesian box, non-periodic, dense neutral slab (n_H = 1 cm^-3) with a 5e54/s source at the "
+                f"-x face centre, {args.dirs} directions, {args.levels} timestep levels, max_timestep 1 Myr (BASELINE.json configs[3])")
+    else:
+        text = (f"{args.n}^3-cell periodic box ({args.grid}), log-normal density, "
+                f"{max(1, int(round(64 * (args.n / 128.0) ** 3)))} point sources of 1e52/s, {args.dirs} directions, "
+                f"{args.levels} timestep levels, max_timestep 1 Myr (BASELINE.json configs[1])")
     cfg = {
-        "workload": f"{args.n}^3-cell periodic box ({args.grid}), log-normal density, "
-                    f"{max(1, int(round(64 * (args.n / 128.0) ** 3)))} point sources of 1e52/s, {args.dirs} directions, "
-                    f"{args.levels} timestep levels, max_timestep 1 Myr (BASELINE.json configs[1])",
+        "workload": text,
         "cells": args.n ** 3, "directions": args.dirs, "timestep_levels": args.levels, "grid": args.grid,
         "parallelism": f"direction sharding x{args.gpus}" if args.gpus > 1 else "single GPU",
         "l2": "working set (per-direction flux state + level sets, > 2 GB) is far larger than the 126 MB L2; no flush needed",
@@ -270,9 +299,16 @@ def run_b200(args) -> None:
     if world > 1:
         dist.barrier()
 
-    params, g, fields = build_workload(args.n, args.grid, args.dirs, args.levels)
+    params, g, fields = build_workload(args.n, args.grid, args.dirs, args.levels, args.workload)
     allreduce = make_allreduce(device) if world > 1 else None
-    sweep = Sweep(params, g, **fields, device_id=local_rank, rank=rank, world_size=world, allreduce=allreduce)
+    shard_rank, shard_world = rank, world
+    if args.emulate_shard and world == 1:
+        # profiling aid: one GPU runs rank 0's direction shard of a W-rank job with a no-op all-reduce, to tune the
+        # kernels at the per-GPU work of a multi-GPU run without holding W GPUs (results are NOT a bench line)
+        shard_rank, shard_world = 0, args.emulate_shard
+        allreduce = lambda ptr, n, stream: None   # noqa: E731
+        args.no_e2e = True
+    sweep = Sweep(params, g, **fields, device_id=local_rank, rank=shard_rank, world_size=shard_world, allreduce=allreduce)
     N = g.n_cells
     b_alg, f_up = algorithmic_bytes_per_update(g, sweep.directions.xyz)
 
@@ -360,8 +396,16 @@ def run_b200(args) -> None:
     k_tasks = tim["kernel_level_tasks"][lvl]
     k_launches = max(1, tim["kernel_level_launches"][lvl])
     achieved = (b_alg * k_tasks / (k_ms * 1e-3)) / 1e9 if k_ms > 0 else 0.0
+    # measured DRAM traffic of the same kernel on the same workload, from the committed ncu --set full capture
+    traffic, traffic_source = None, None
+    tfile = ROOT / "profiles" / "roofline_traffic.json"
+    if tfile.exists() and world == 1 and (args.n, args.grid, args.dirs, args.workload) == (128, "cartesian", 84, "box"):
+        t = json.loads(tfile.read_text())
+        traffic, traffic_source = t["dram_bytes_per_launch"], t["source"]
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": traffic_source,
+        "algorithmic_bytes_per_launch": b_alg * k_tasks / k_launches,
         "kernel": "sweep kernel of the all-cells single sweep (timestep level %d)" % lvl,
         "algorithmic_bytes_per_update": b_alg, "mean_upwind_faces": f_up,
         "updates_per_launch": k_tasks / k_launches, "ms_per_launch": k_ms / k_launches, "peak_source": peak_kind,
@@ -370,7 +414,7 @@ def run_b200(args) -> None:
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
-        v, _, sample, _ = cpu_run(args.cpu_n, args.grid, args.dirs, args.levels, 2, args.warmup, threads)
+        v, _, sample, _ = cpu_run(args.cpu_n, args.grid, args.dirs, args.levels, 2, args.warmup, threads, args.workload)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
 
     line = {
@@ -408,8 +452,12 @@ def main() -> None:
     ap.add_argument("--grid", choices=("cartesian", "voronoi"), default="cartesian")
     ap.add_argument("--dirs", type=int, default=84)
     ap.add_argument("--levels", type=int, default=4)
+    ap.add_argument("--workload", choices=("box", "front"), default="box",
+                    help="box: BASELINE.json configs[1] (default); front: configs[3], the chemistry-stiff ionization front")
     ap.add_argument("--cpu-n", type=int, default=48, help="cells per dimension of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-shard", type=int, default=0, metavar="W",
+                    help="profiling only: run rank 0's direction shard of a W-rank job on one GPU (no-op all-reduce)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: stop after the device-timed region")
     args = ap.parse_args()
     if args.warmup < 3:
