@@ -454,7 +454,7 @@ def main() -> None:
     ap.add_argument("--levels", type=int, default=4)
     ap.add_argument("--workload", choices=("box", "front"), default="box",
                     help="box: BASELINE.json configs[1] (default); front: configs[3], the chemistry-stiff ionization front")
-    ap.add_argument("--cpu-n", type=int, default=48, help="cells per dimension of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=96, help="cells per dimension of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--emulate-shard", type=int, default=0, metavar="W",
                     help="profiling only: run rank 0's direction shard of a W-rank job on one GPU (no-op all-reduce)")

@@ -744,8 +744,12 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
     const uint32_t n = (uint32_t)n_tasks;
     const uint32_t n_dl = (uint32_t)n_local_dirs;
     // tunables (environment overrides are for experiments; DESIGN.md section 5 lists the defaults)
-    const uint32_t threads = env_u32("SSW_STREAM_THREADS", 256) == 256 ? 256u : 512u;
-    uint32_t G = std::min<uint32_t>(env_u32("SSW_STREAM_GROUPS", 2), kMaxGroups);
+    // few local directions (a direction shard of a multi-GPU job): the sweep is bound by the latency of its
+    // level barriers, fewer and larger blocks with a single direction group cross them fastest (measured at
+    // 10 and 21 directions); otherwise 256-thread blocks, 4 per SM, two interleaved groups
+    const bool few_dirs = n_dl <= 24;
+    const uint32_t threads = env_u32("SSW_STREAM_THREADS", few_dirs ? 512 : 256) == 256 ? 256u : 512u;
+    uint32_t G = std::min<uint32_t>(env_u32("SSW_STREAM_GROUPS", few_dirs ? 1 : 2), kMaxGroups);
     G = std::max<uint32_t>(1u, std::min<uint32_t>(G, n_dl));
     uint32_t want_bps = env_u32("SSW_STREAM_BPS", threads == 256 ? 4 : 2);
     const uint32_t want_stages = std::max<uint32_t>(1u, std::min<uint32_t>(env_u32("SSW_STREAM_STAGES", 3), kMaxStages));
