@@ -67,7 +67,9 @@ typedef struct ssw_params {
 
 enum {
     SSW_FLAG_NO_SCHEDULE_CACHE = 1u << 0, /* rebuild wavefront level sets every single sweep      */
-    SSW_FLAG_NO_COMPILED_PATH = 1u << 1   /* replay cached level sets from the generic task list   */
+    SSW_FLAG_NO_COMPILED_PATH = 1u << 1,  /* replay cached level sets from the generic task list   */
+    SSW_FLAG_NO_PATCH_PATH = 1u << 2      /* keep the level-barrier stream even when cell positions */
+                                          /* are known (ssw_set_cell_positions)                     */
 };
 
 /* Flat (CSR) form of the per-particle `Cell` component (src/sweep/grid/cell.rs:92-133):
@@ -122,6 +124,16 @@ int ssw_create(const ssw_params *params, const ssw_grid *grid, const double *den
 /* Drop (src/sweep/communicator.rs:116-125). */
 void ssw_destroy(ssw_handle *h);
 int ssw_set_allreduce(ssw_handle *h, ssw_allreduce_fn fn, void *ctx);
+/* Optional, once, before the first ssw_run_sweeps: the `Position` component of every cell
+ * (src/components.rs, N x 3, cell order).  The solver itself never needs positions
+ * (Sweep::new does not take them, src/sweep/mod.rs:194-232); they let the library group cells into
+ * spatial patches and run the all-cells sweep as a dataflow of (patch, direction group) macro-tiles
+ * without device-wide barriers.  Results do not depend on whether positions
+ * were given beyond round-off in the per-cell rate sums.  Grids whose patches depend on each other
+ * cyclically keep the level-barrier form; ssw_patch_note() says why (empty string: patch form in use
+ * or not tried). */
+int ssw_set_cell_positions(ssw_handle *h, const double *xyz /* N x 3 */);
+const char *ssw_patch_note(ssw_handle *h);
 
 /* -- the hot path ------------------------------------------------------------------------ */
 
@@ -186,7 +198,9 @@ typedef enum ssw_stat {
     SSW_STAT_KERNEL_LAUNCHES = 6,   /* kernels launched by this library since create            */
     SSW_STAT_WAVEFRONT_LEVELS = 7,  /* level count of the last single sweep                     */
     SSW_STAT_CHEM_ATTEMPTS = 8,     /* try_timestep_update calls                                 */
-    SSW_STAT_CHEM_MAX_DEPTH = 9
+    SSW_STAT_CHEM_MAX_DEPTH = 9,
+    SSW_STAT_PATCH_MACRO_TILES = 10, /* macro-tiles of the patch-ordered all-cells sweep (0: not in use) */
+    SSW_STAT_PATCH_LEVELS = 11       /* dependent macro-tile levels (vs SSW_STAT_WAVEFRONT_LEVELS)       */
 } ssw_stat;
 int ssw_get_stat(ssw_handle *h, ssw_stat which, uint64_t *out);
 

@@ -14,7 +14,7 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "libsubsweep_b200.so"
 
 SSW_OK, SSW_E_INVALID, SSW_E_CUDA, SSW_E_DEADLOCK, SSW_E_NOMEM, SSW_E_COMM = 0, -1, -2, -3, -4, -5
 FACE_LOCAL, FACE_BOUNDARY, FACE_LOCAL_PERIODIC = 0, 1, 2
-FLAG_NO_SCHEDULE_CACHE, FLAG_NO_COMPILED_PATH = 1, 2
+FLAG_NO_SCHEDULE_CACHE, FLAG_NO_COMPILED_PATH, FLAG_NO_PATCH_PATH = 1, 2, 4
 
 FIELDS = {
     "ionized_hydrogen_fraction": 0, "temperature": 1, "timestep": 2, "photon_rate": 3,
@@ -25,7 +25,7 @@ FIELDS = {
 STATS = {
     "tasks_solved": 0, "single_sweeps": 1, "chem_cells": 2, "chem_failures": 3, "schedule_builds": 4,
     "schedule_replays": 5, "kernel_launches": 6, "wavefront_levels": 7, "chem_attempts": 8,
-    "chem_max_depth": 9,
+    "chem_max_depth": 9, "patch_macro_tiles": 10, "patch_levels": 11,
 }
 
 c_double_p = C.POINTER(C.c_double)
@@ -83,6 +83,8 @@ SYMBOLS = {
     "ssw_create": (C.c_int, [C.POINTER(Params), C.POINTER(Grid), c_double_p, c_double_p, c_double_p, c_double_p, C.POINTER(H)]),
     "ssw_destroy": (None, [H]),
     "ssw_set_allreduce": (C.c_int, [H, ALLREDUCE_FN, C.c_void_p]),
+    "ssw_set_cell_positions": (C.c_int, [H, c_double_p]),
+    "ssw_patch_note": (C.c_char_p, [H]),
     "ssw_run_sweeps": (C.c_int, [H, c_double_p]),
     "ssw_set_inputs": (C.c_int, [H, c_double_p, c_double_p]),
     "ssw_read": (C.c_int, [H, C.c_int, c_double_p]),

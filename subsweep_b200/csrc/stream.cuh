@@ -105,6 +105,8 @@ __host__ __device__ inline TileLayout tile_layout(uint32_t n, uint32_t E) {
     return L;
 }
 
+struct PDesc;   // patch.cuh
+
 struct Compiled {
     bool valid = false;
     uint64_t n_tasks = 0;           // real tasks (slots with an outgoing rate)
@@ -131,7 +133,14 @@ struct Compiled {
     uint32_t *lvl_dep = nullptr;    // n_pl: pseudo-level that must be complete first (kNoDep: none)
     unsigned int *lvl_count = nullptr; // n_pl arrival counters
     double *acc_cell = nullptr;     // G x N: sum_d incoming of the group's directions
-    double *acc_per = nullptr;      // G x n_periodic: sum_d periodic_source
+    double *acc_per = nullptr;      // G x n_periodic: sum_d periodic_source (patch mode: one row)
+    // patch-ordered form (patch.cuh): macro-tiles (patch, direction group) with point-to-point done flags
+    bool patch_mode = false;
+    uint32_t n_groups_per = 1;      // rows of acc_per
+    uint32_t n_mt = 0, vmax = 0, pc_max = 0, epoch = 0;
+    uint32_t kd = 0, n_patches = 0, patch_levels = 0;
+    unsigned int *mt_flag = nullptr;   // n_mt: epoch of the sweep that last completed the macro-tile
+    PDesc *ptab = nullptr;             // packet table, block-major
     Compiled() = default;
     Compiled(const Compiled &) = delete;
     Compiled &operator=(const Compiled &) = delete;
@@ -139,7 +148,10 @@ struct Compiled {
     void release() {
         cudaFree(slot_of); cudaFree(out_slot); cudaFree(ttot_slot); cudaFree(lag_src); cudaFree(stream);
         cudaFree(tab); cudaFree(tab_off); cudaFree(stream_off); cudaFree(lvl_target); cudaFree(lvl_dep);
-        cudaFree(lvl_count); cudaFree(acc_cell); cudaFree(acc_per);
+        cudaFree(lvl_count); cudaFree(acc_cell); cudaFree(acc_per); cudaFree(mt_flag); cudaFree(ptab);
+        mt_flag = nullptr;
+        ptab = nullptr;
+        patch_mode = false;
         slot_of = lag_src = tab_off = lvl_target = lvl_dep = nullptr;
         out_slot = ttot_slot = acc_cell = acc_per = nullptr;
         stream = nullptr;
@@ -445,7 +457,8 @@ s_lag_snapshot_kernel(const uint32_t *__restrict__ lag_src, uint32_t n_lag, uint
 // rate_act[c] = sum_d ((incoming[d] + source / D) + periodic_source[d]) over this rank's directions
 // (src/sweep/mod.rs:554-558, site.rs:53-56) from the group accumulators of the compiled sweep
 __global__ void __launch_bounds__(256)
-s_rate_finish_kernel(uint32_t n_cells, uint32_t n_groups, uint32_t n_periodic, int n_local_dirs, double n_dirs_total,
+s_rate_finish_kernel(uint32_t n_cells, uint32_t n_groups, uint32_t n_groups_per, uint32_t n_periodic, int n_local_dirs,
+                     double n_dirs_total,
                      const double *__restrict__ acc_cell, const double *__restrict__ acc_per,
                      const int32_t *__restrict__ pidx, const double *__restrict__ src, double *__restrict__ rate_act,
                      double *__restrict__ photon) {
@@ -459,7 +472,7 @@ s_rate_finish_kernel(uint32_t n_cells, uint32_t n_groups, uint32_t n_periodic, i
     const int32_t p = pidx[c];
     if (p >= 0) {
         double per = 0.0;
-        for (uint32_t g = 0; g < n_groups; ++g) per += acc_per[(size_t)g * n_periodic + p];
+        for (uint32_t g = 0; g < n_groups_per; ++g) per += acc_per[(size_t)g * n_periodic + p];
         rate += per;
     }
     rate_act[c] = rate + (src[c] / n_dirs_total) * (double)n_local_dirs;
@@ -1029,6 +1042,7 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
     C.n_tasks = n_tasks;
     C.n_levels = n_levels;
     C.n_groups = G;
+    C.n_groups_per = G;
     C.n_pl = n_pl;
     C.n_cells = g.n_cells;
     C.n_periodic = n_periodic;

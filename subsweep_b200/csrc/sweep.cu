@@ -20,6 +20,7 @@
 #include "../../include/subsweep_b200.h"
 #include "kernels.cuh"
 #include "stream.cuh"
+#include "patch.cuh"
 
 namespace ssw {
 
@@ -79,6 +80,7 @@ struct DevBuf {
 };
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+static inline uint32_t stream_env_u32(const char *name, uint32_t fallback) { return env_u32(name, fallback); }
 
 // ------------------------------------------------------------------------------------------
 // wavefront level sets of one active set
@@ -130,6 +132,12 @@ struct Sweep {
     DevBuf<int32_t> pidx;
     DevBuf<uint32_t> pcells;
     uint32_t n_periodic = 0;
+    // spatial patches (ssw_set_cell_positions): cell -> patch map of the patch-ordered all-cells sweep (patch.cuh)
+    DevBuf<uint32_t> patch_of, patch_off, patch_cells;
+    DevBuf<uint16_t> patch_lidx;
+    uint32_t n_patches = 0, patch_max_cells = 0;
+    bool have_patches = false;
+    std::string patch_note;   // why the patch-ordered form is not in use (empty: it is, or was never tried)
     // per (dir, cell)
     DevBuf<double> q, incoming;
     DevBuf<int32_t> missing;
@@ -281,6 +289,13 @@ struct Sweep {
 
     void create(const ssw_params *p, const ssw_grid *g, const double *density, const double *xhii,
                 const double *temperature, const double *source);
+    void set_positions(const double *xyz);
+    PatchGrid patch_view() const {
+        PatchGrid pg;
+        pg.patch_of = patch_of.p; pg.lidx = patch_lidx.p; pg.patch_off = patch_off.p; pg.patch_cells = patch_cells.p;
+        pg.n_patches = n_patches; pg.max_cells = patch_max_cells;
+        return pg;
+    }
     void refresh_histogram();
     void build_active_list(Schedule &S, int cur);
     void gather_periodic(double *dst, const uint32_t *act, uint32_t n_act);
@@ -446,6 +461,84 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     coop_blocks_replay = coop_grid((const void *)sweep_replay_kernel, 256, num_sms);
     coop_blocks_mini = coop_grid((const void *)mini_replay_kernel, 256, num_sms);
     CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+// Cell centres -> spatial patches: boxes of a regular lattice over the bounding box of the centres, sized for
+// about SSW_PATCH_CELLS (512) cells each.  Host preprocessing, once per grid.
+void Sweep::set_positions(const double *xyz) {
+    if (!xyz) fail(SSW_E_INVALID, "null positions");
+    have_patches = false;
+    patch_note.clear();
+    if (state) fail(SSW_E_INVALID, "cell positions must be set before the first all-cells schedule is compiled");
+    double lo[3], hi[3];
+    for (int k = 0; k < 3; ++k) { lo[k] = std::numeric_limits<double>::infinity(); hi[k] = -lo[k]; }
+    for (uint32_t c = 0; c < N; ++c)
+        for (int k = 0; k < 3; ++k) {
+            const double v = xyz[3 * (size_t)c + k];
+            if (!std::isfinite(v)) fail(SSW_E_INVALID, "cell %u: position is not finite", c);
+            lo[k] = std::min(lo[k], v);
+            hi[k] = std::max(hi[k], v);
+        }
+    int dims = 0;
+    double vol = 1.0;
+    for (int k = 0; k < 3; ++k)
+        if (hi[k] > lo[k]) { ++dims; vol *= hi[k] - lo[k]; }
+    double target = (double)stream_env_u32("SSW_PATCH_CELLS", 512);
+    target = std::min<double>(std::max<double>(target, 8.0), (double)kMaxPatchCells);
+    std::vector<uint32_t> pof(N), poff, pcl(N);
+    std::vector<uint16_t> lidx(N);
+    for (int attempt = 0; attempt < 8; ++attempt, target *= 0.5) {
+        uint32_t nbx[3] = {1, 1, 1};
+        double org[3] = {lo[0], lo[1], lo[2]}, width[3] = {1.0, 1.0, 1.0};
+        if (dims > 0) {
+            const double spacing = std::pow(vol / (double)N, 1.0 / dims);   // mean distance of neighbouring centres
+            double vol_ext = 1.0;
+            for (int k = 0; k < 3; ++k)
+                if (hi[k] > lo[k]) vol_ext *= hi[k] - lo[k] + spacing;
+            const double edge = std::pow(vol_ext * target / (double)N, 1.0 / dims);
+            for (int k = 0; k < 3; ++k) {
+                if (!(hi[k] > lo[k])) continue;
+                const double len = hi[k] - lo[k] + spacing;
+                nbx[k] = (uint32_t)std::max<double>(1.0, std::min<double>(1024.0, std::floor(len / edge + 0.5)));
+                org[k] = lo[k] - 0.5 * spacing;
+                width[k] = len / nbx[k];
+            }
+        }
+        const uint64_t P64 = (uint64_t)nbx[0] * nbx[1] * nbx[2];
+        if (P64 > (1u << 20)) { patch_note = "more than 2^20 patches"; return; }
+        const uint32_t Pn = (uint32_t)P64;
+        std::vector<uint32_t> count(Pn, 0);
+        for (uint32_t c = 0; c < N; ++c) {
+            uint32_t b[3];
+            for (int k = 0; k < 3; ++k) {
+                const double t = (xyz[3 * (size_t)c + k] - org[k]) / width[k];
+                b[k] = (uint32_t)std::min<double>((double)nbx[k] - 1.0, std::max<double>(0.0, std::floor(t)));
+            }
+            pof[c] = (b[0] * nbx[1] + b[1]) * nbx[2] + b[2];
+            count[pof[c]]++;
+        }
+        const uint32_t mx = *std::max_element(count.begin(), count.end());
+        if (mx > kMaxPatchCells) continue;
+        poff.assign((size_t)Pn + 1, 0);
+        for (uint32_t p = 0; p < Pn; ++p) poff[p + 1] = poff[p] + count[p];
+        std::vector<uint32_t> cur(poff.begin(), poff.end() - 1);
+        for (uint32_t c = 0; c < N; ++c) {
+            const uint32_t pos = cur[pof[c]]++;
+            pcl[pos] = c;
+            lidx[c] = (uint16_t)(pos - poff[pof[c]]);
+        }
+        CUDA_CHECK(cudaSetDevice(device));
+        patch_of.alloc(N); patch_of.upload(pof.data(), N, stream);
+        patch_lidx.alloc(N); patch_lidx.upload(lidx.data(), N, stream);
+        patch_off.alloc((size_t)Pn + 1); patch_off.upload(poff.data(), (size_t)Pn + 1, stream);
+        patch_cells.alloc(N); patch_cells.upload(pcl.data(), N, stream);
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        n_patches = Pn;
+        patch_max_cells = mx;
+        have_patches = true;
+        return;
+    }
+    patch_note = "no patch lattice with <= 1024 cells per patch";
 }
 
 void Sweep::refresh_histogram() {
@@ -644,8 +737,23 @@ void Sweep::single_sweep(int cur) {
         if (use_compiled && !S.compiled.valid) {
             const size_t t_sched = tic(T_SCHED);
             try {
-                compile_schedule(S.compiled, grid_view(), S.tasks.p, S.level_off.p, S.n_tasks, S.n_levels, Dl,
-                                 pcells.p, n_periodic, pidx.p, q.p, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
+                bool patched = false;
+                if (have_patches && !(P.flags & SSW_FLAG_NO_PATCH_PATH) && stream_env_u32("SSW_PATCH", 1)) {
+                    try {
+                        compile_patch_schedule(S.compiled, grid_view(), patch_view(), dirs_all.data() + 3 * (size_t)d0,
+                                               S.tasks.p, S.level_off.p, S.n_tasks, S.n_levels, Dl, n_periodic, q.p,
+                                               num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
+                        patched = true;
+                        patch_note.clear();
+                        stat[SSW_STAT_PATCH_MACRO_TILES] = S.compiled.n_mt;
+                        stat[SSW_STAT_PATCH_LEVELS] = S.compiled.patch_levels;
+                    } catch (const PatchUnsupported &e) {
+                        patch_note = e.what();   // keep the level-barrier stream
+                    }
+                }
+                if (!patched)
+                    compile_schedule(S.compiled, grid_view(), S.tasks.p, S.level_off.p, S.n_tasks, S.n_levels, Dl,
+                                     pcells.p, n_periodic, pidx.p, q.p, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
             } catch (const std::exception &e) {
                 fail(SSW_E_CUDA, "%s", e.what());
             }
@@ -659,8 +767,12 @@ void Sweep::single_sweep(int cur) {
             try {
                 cellrec_kernel<<<cdiv(N, 256), 256, 0, stream>>>(att.p, src.p, (double)D, N, cellrec.p);
                 launched();
-                run_compiled(S.compiled, cellrec.p, P.significant_rate_threshold_per_s, stream,
-                             &stat[SSW_STAT_KERNEL_LAUNCHES]);
+                if (S.compiled.patch_mode)
+                    run_patch(S.compiled, grid_view(), pcells.p, cellrec.p, P.significant_rate_threshold_per_s, stream,
+                              &stat[SSW_STAT_KERNEL_LAUNCHES]);
+                else
+                    run_compiled(S.compiled, cellrec.p, P.significant_rate_threshold_per_s, stream,
+                                 &stat[SSW_STAT_KERNEL_LAUNCHES]);
             } catch (const std::exception &e) {
                 fail(SSW_E_CUDA, "%s", e.what());
             }
@@ -709,7 +821,7 @@ void Sweep::single_sweep(int cur) {
     if (use_compiled && S.compiled.valid) {
         // the compiled sweep left sum_d incoming and sum_d periodic_source in its group accumulators
         const Compiled &C = S.compiled;
-        s_rate_finish_kernel<<<cdiv(N, 256), 256, 0, stream>>>(N, C.n_groups, n_periodic, Dl, (double)D, C.acc_cell,
+        s_rate_finish_kernel<<<cdiv(N, 256), 256, 0, stream>>>(N, C.n_groups, C.n_groups_per, n_periodic, Dl, (double)D, C.acc_cell,
                                                                C.acc_per, pidx.p, src.p, rate_act.p, photon.p);
         photon_valid = true;
     } else {
@@ -903,6 +1015,15 @@ int ssw_set_allreduce(ssw_handle *h, ssw_allreduce_fn fn, void *ctx) {
     h->s.allreduce_ctx = ctx;
     SSW_CATCH
 }
+
+int ssw_set_cell_positions(ssw_handle *h, const double *xyz) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    h->s.set_positions(xyz);
+    SSW_CATCH
+}
+
+const char *ssw_patch_note(ssw_handle *h) { return h ? h->s.patch_note.c_str() : ""; }
 
 int ssw_run_sweeps(ssw_handle *h, double *time_elapsed_s) {
     SSW_TRY

@@ -107,7 +107,8 @@ class Sweep:
 
     def __init__(self, parameters: SweepParameters, grid: FlatGrid, density, ionized_hydrogen_fraction,
                  temperature, source, scale_factor: float = 1.0, device_id: int = 0, rank: int = 0,
-                 world_size: int = 1, allreduce: Optional[AllReduce] = None, flags: int = 0, lib=None):
+                 world_size: int = 1, allreduce: Optional[AllReduce] = None, flags: int = 0, lib=None,
+                 positions="grid"):
         if parameters.rotate_directions:
             raise NotImplementedError("rotate_directions is not supported yet (DESIGN.md, out of scope)")
         self.lib = lib if lib is not None else capi.load()
@@ -157,6 +158,14 @@ class Sweep:
         self._h = C.c_void_p()
         self._check(self.lib.ssw_create(C.byref(p), C.byref(g), *(capi.dptr(a) for a in arrs), C.byref(self._h)))
         self._cb = None
+        # the Position component (optional): lets the library run the all-cells sweep patch by patch
+        if isinstance(positions, str):
+            positions = getattr(grid, "positions", None) if positions == "grid" else None
+        if positions is not None:
+            pos = np.ascontiguousarray(positions, dtype=np.float64)
+            if pos.shape != (N, 3):
+                raise ValueError("positions must have shape (n_cells, 3)")
+            self._check(self.lib.ssw_set_cell_positions(self._h, capi.dptr(pos)))
         if world_size > 1:
             if allreduce is None:
                 raise ValueError("world_size > 1 needs an allreduce callable")
@@ -271,6 +280,10 @@ class Sweep:
         self._check(self.lib.ssw_read_wavefront_levels(self._h, level, direction,
                                                        out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
+
+    def patch_note(self) -> str:
+        """Why the patch-ordered all-cells sweep is not in use ('' = in use, or not tried yet)."""
+        return (self.lib.ssw_patch_note(self._h) or b"").decode()
 
     def stat(self, name: str) -> int:
         v = C.c_uint64()

@@ -51,7 +51,7 @@ def test_wavefront_levels_closed_form(cuda_lib, box):
 def test_compiled_and_generic_paths_agree_at_full_size(cuda_lib, box):
     params, g, f = box
     results = {}
-    for name, flags in (("compiled", 0), ("generic", capi.FLAG_NO_COMPILED_PATH)):
+    for name, flags in (("compiled", 0), ("stream", capi.FLAG_NO_PATCH_PATH), ("generic", capi.FLAG_NO_COMPILED_PATH)):
         s = Sweep(params, g, **f, flags=flags)
         for _ in range(5):
             s.run_sweeps()
@@ -63,10 +63,16 @@ def test_compiled_and_generic_paths_agree_at_full_size(cuda_lib, box):
         assert counts[0] == g.n_cells and np.all(np.diff(counts.astype(np.int64)) <= 0)
         assert s.stat("tasks_solved") >= 5 * g.n_cells * 84
         assert s.stat("chem_failures") == 0
+        # the default is the patch-ordered dataflow: 46 dependent macro-tile levels instead of 382 wavefront levels
+        assert (s.stat("patch_macro_tiles") > 0) == (name == "compiled"), s.patch_note()
+        if name == "compiled":
+            assert s.stat("patch_levels") == 46
         s.close()
-    a, b = results["compiled"], results["generic"]
-    assert np.array_equal(a["levels"], b["levels"]) and np.array_equal(a["counts"], b["counts"])
-    for k in ("ionized_hydrogen_fraction", "temperature", "change_timescale", "photon_rate"):
-        assert_close(a[k], b[k], 1e-10, floor=1e-7 * np.nanmax(np.abs(b[k])), what=k)
+    b = results["generic"]
+    for a in (results["compiled"], results["stream"]):
+        assert np.array_equal(a["levels"], b["levels"]) and np.array_equal(a["counts"], b["counts"])
+        for k in ("ionized_hydrogen_fraction", "temperature", "change_timescale", "photon_rate"):
+            assert_close(a[k], b[k], 1e-10, floor=1e-7 * np.nanmax(np.abs(b[k])), what=k)
+    a = results["compiled"]
     x = a["ionized_hydrogen_fraction"]
     assert 1e-10 <= x.min() and x.max() <= 1.0 - 1e-10 and x.max() > 0.5      # the sources ionize their surroundings

@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("kind,n,periodic", [("cartesian", 12, True), ("voronoi", 9, True), ("voronoi", 9, False)])
 def test_all_paths_bitwise_identical(cuda_lib, kind, n, periodic):
     params, g, f = make_problem(kind, n, periodic, n_dirs=21, n_levels=3, max_timestep_myr=0.25)
-    variants = {"default": 0, "no_cache": capi.FLAG_NO_SCHEDULE_CACHE, "no_compiled": capi.FLAG_NO_COMPILED_PATH}
+    variants = {"default": 0, "no_cache": capi.FLAG_NO_SCHEDULE_CACHE, "no_compiled": capi.FLAG_NO_COMPILED_PATH,
+                "no_patch": capi.FLAG_NO_PATCH_PATH}
     results = {}
     for name, flags in variants.items():
         s = Sweep(params, g, **f, flags=flags)
@@ -29,12 +30,14 @@ def test_all_paths_bitwise_identical(cuda_lib, kind, n, periodic):
     # fused build+solve and cached replay do the same arithmetic per task: bit-identical
     for k, v in results["no_cache"].items():
         assert np.array_equal(v, results["no_compiled"][k], equal_nan=True), k
-    # the compiled path folds 1 / sum_downwind(A n.d) into its precomputed shares: round-off only
-    for k, v in results["default"].items():
-        if k == "levels":
-            assert np.array_equal(v, results["no_compiled"][k])
-        else:
-            assert_close(v, results["no_compiled"][k], 1e-11, floor=1e-7 * np.nanmax(np.abs(v)), what=k)
+    # the compiled paths (patch-ordered dataflow where the grid admits it, level-barrier stream otherwise) fold
+    # 1 / sum_downwind(A n.d) into their precomputed shares: round-off only
+    for name in ("default", "no_patch"):
+        for k, v in results[name].items():
+            if k == "levels":
+                assert np.array_equal(v, results["no_compiled"][k])
+            else:
+                assert_close(v, results["no_compiled"][k], 1e-11, floor=1e-7 * np.nanmax(np.abs(v)), what=k)
 
 
 def test_sweep_plugin_surface(cuda_lib):
