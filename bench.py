@@ -358,6 +358,9 @@ def run_b200(args) -> None:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": dev_ms / args.steps,
                               "all_cells_sweep_ms": tim["kernel_level_ms"][lvl0] / max(1, tim["kernel_level_launches"][lvl0]),
                               "sweep_ms": tim["sweep_ms"] / args.steps, "chemistry_ms": tim["chemistry_ms"] / args.steps,
+                              "all_cells_form": "patch dataflow" if sweep.stat("patch_macro_tiles") else "level-barrier stream (" + (sweep.patch_note() or "patch form off") + ")",
+                              "macro_tiles": sweep.stat("patch_macro_tiles"), "patch_levels": sweep.stat("patch_levels"),
+                              "mean_xhii": float(sweep.read("ionized_hydrogen_fraction").mean()),
                               "env": {k: v for k, v in os.environ.items() if k.startswith("SSW_")},
                               "note": "profiling run (--no-e2e): not a bench line"}), flush=True)
         return
@@ -406,7 +409,8 @@ def run_b200(args) -> None:
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": traffic_source,
         "algorithmic_bytes_per_launch": b_alg * k_tasks / k_launches,
-        "kernel": "sweep kernel of the all-cells single sweep (timestep level %d)" % lvl,
+        "kernel": ("patch_sweep_kernel (macro-tile dataflow, %d macro-tiles in %d dependent levels)" % (sweep.stat("patch_macro_tiles"), sweep.stat("patch_levels"))
+                   if sweep.stat("patch_macro_tiles") else "sweep_stream_kernel (level-barrier stream)") + " of the all-cells single sweep (timestep level %d)" % lvl,
         "algorithmic_bytes_per_update": b_alg, "mean_upwind_faces": f_up,
         "updates_per_launch": k_tasks / k_launches, "ms_per_launch": k_ms / k_launches, "peak_source": peak_kind,
     }
@@ -437,7 +441,11 @@ def run_b200(args) -> None:
                    "level_counts": [int(v) for v in sweep.level_counts()],
                    "chem_attempts": sweep.stat("chem_attempts"), "chem_cells": sweep.stat("chem_cells"),
                    "chem_max_depth": sweep.stat("chem_max_depth"), "wavefront_levels": sweep.stat("wavefront_levels"),
-                   "schedule_builds": sweep.stat("schedule_builds"), "schedule_replays": sweep.stat("schedule_replays")},
+                   "schedule_builds": sweep.stat("schedule_builds"), "schedule_replays": sweep.stat("schedule_replays"),
+                   "patch_macro_tiles": sweep.stat("patch_macro_tiles"), "patch_levels": sweep.stat("patch_levels"),
+                   "patch_note": sweep.patch_note(),
+                   "checksum": {"mean_xhii": float(outs["ionized_hydrogen_fraction"].mean()),
+                                "mean_temperature": float(outs["temperature"].mean())}},
     }
     print(json.dumps(line), flush=True)
 

@@ -88,8 +88,8 @@ struct __align__(16) PHdr {
     uint16_t b16;      // tile: bit 0 = last tile of the macro-tile, bits 8.. = shuffle steps; head: direction group
     uint32_t c32;      // tile: first slot of the tile inside the macro-tile; head: external entries
     uint32_t next_off16, next_bytes;   // packet that goes into this ring stage next (bytes = 0: none)
-    uint32_t gslot0;   // head: first global slot of the macro-tile
-    uint32_t n_slots;  // head: slots of the macro-tile
+    uint32_t gslot0;   // head: first global slot of the macro-tile; tile: idx offset | lcell offset << 16 (16-B units)
+    uint32_t n_slots;  // head: slots of the macro-tile; tile: info offset (16-B units)
     uint32_t rank;     // head: index of the macro-tile's done flag
 };
 static_assert(sizeof(PHdr) == 32, "packet header is 32 bytes");
@@ -399,6 +399,8 @@ p_fill_kernel(PFillArgs a) {
         h.kind = 0; h.n = (uint16_t)n; h.a16 = (uint16_t)E;
         h.b16 = (uint16_t)(((d.flags & kPLast) ? 1u : 0u) | (steps << 8));
         h.c32 = slot0 - mt0;
+        h.gslot0 = (L.idx >> 4) | ((L.lcell >> 4) << 16);   // tile packets: section offsets in 16-B units
+        h.n_slots = L.info >> 4;
         *reinterpret_cast<PHdr *>(pkt) = h;
     }
 }
@@ -540,13 +542,12 @@ patch_sweep_kernel(PatchArgs a) {
             }
         } else {
             // ---- one tile: <= THREADS tasks of one sub-level; every value it reads is in shared memory
-            const uint32_t n = h.n, E = h.a16, lslot0 = h.c32;
+            const uint32_t n = h.n, lslot0 = h.c32;
             const uint32_t scan_steps = h.b16 >> 8;
-            const PTileLayout L = ptile_layout(n, E);
-            const double *const w = reinterpret_cast<const double *>(pkt + L.w);
-            const uint16_t *const idx = reinterpret_cast<const uint16_t *>(pkt + L.idx);
-            const uint16_t *const lcell = reinterpret_cast<const uint16_t *>(pkt + L.lcell);
-            const uint32_t *const info = reinterpret_cast<const uint32_t *>(pkt + L.info);
+            const double *const w = reinterpret_cast<const double *>(pkt + sizeof(PHdr));
+            const uint16_t *const idx = reinterpret_cast<const uint16_t *>(pkt + ((h.gslot0 & 0xffffu) << 4));
+            const uint16_t *const lcell = reinterpret_cast<const uint16_t *>(pkt + ((h.gslot0 >> 16) << 4));
+            const uint32_t *const info = reinterpret_cast<const uint32_t *>(pkt + (h.n_slots << 4));
             uint32_t lc = 0xffffffffu, inf = 0;
             double inc = 0.0;
             if (tid < n) {
@@ -558,11 +559,26 @@ patch_sweep_kernel(PatchArgs a) {
                 const uint32_t em = e1 - ((inf >> 16) & 0xffu);
                 double in_loc = 0.0, in_per = 0.0;
                 // product and sum rounded separately, Local faces in face order, then the periodic ones: the
-                // arithmetic of stream.cuh bit for bit
-#pragma unroll 1
-                for (; e < em; ++e) in_loc = __dadd_rn(in_loc, __dmul_rn(val[idx[e]], w[e]));
-#pragma unroll 1
-                for (; e < e1; ++e) in_per = __dadd_rn(in_per, __dmul_rn(val[idx[e]], w[e]));
+                // arithmetic of stream.cuh bit for bit.  Four entries per round: their loads are independent,
+                // only the additions form a chain.
+                for (; e < e1; e += 4u) {
+                    uint32_t vi[4];
+                    double wv[4], vv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool ok = e + j < e1;
+                        vi[j] = ok ? idx[e + j] : 0u;
+                        wv[j] = ok ? w[e + j] : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) vv[j] = val[vi[j]];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double pr = __dmul_rn(vv[j], wv[j]);
+                        if (e + j < em) in_loc = __dadd_rn(in_loc, pr);
+                        else if (e + j < e1) in_per = __dadd_rn(in_per, pr);
+                    }
+                }
                 inc = in_loc;                                           // incoming_total_rate[d]
                 const double total = (in_loc + rec.y) + in_per;         // site.rs:49-56
                 // HydrogenOnly::get_outgoing_rate, hydrogen_only/mod.rs:81-87
@@ -623,8 +639,9 @@ patch_sweep_kernel(PatchArgs a) {
 
 typedef void (*PatchKernel)(PatchArgs);
 inline PatchKernel patch_kernel_for(uint32_t threads, bool profile) {
-    if (profile) return threads == 128 ? patch_sweep_kernel<128, 1, true> : patch_sweep_kernel<256, 1, true>;
-    return threads == 128 ? patch_sweep_kernel<128, 1, false> : patch_sweep_kernel<256, 1, false>;
+    // minimum blocks per SM chosen so that the register file never limits residency below 1024 threads (<= 64 registers)
+    if (profile) return threads == 64 ? patch_sweep_kernel<64, 16, true> : threads == 128 ? patch_sweep_kernel<128, 8, true> : patch_sweep_kernel<256, 4, true>;
+    return threads == 64 ? patch_sweep_kernel<64, 16, false> : threads == 128 ? patch_sweep_kernel<128, 8, false> : patch_sweep_kernel<256, 4, false>;
 }
 
 template <class T>
@@ -678,7 +695,8 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
     if (n_local_dirs > 128) throw PatchUnsupported("more than 128 local directions");
     if (n_tasks != (uint64_t)g.n_cells * (uint64_t)n_local_dirs) throw PatchUnsupported("not an all-cells schedule");
     const uint32_t n = (uint32_t)n_tasks, n_dl = (uint32_t)n_local_dirs, N = g.n_cells, P = pg.n_patches;
-    const uint32_t threads = env_u32("SSW_PATCH_THREADS", 128) == 256 ? 256u : 128u;
+    const uint32_t threads_env = env_u32("SSW_PATCH_THREADS", 128);
+    const uint32_t threads = threads_env == 256 ? 256u : (threads_env == 64 ? 64u : 128u);
     const uint32_t kd_default = n_dl <= 24 ? 3u : 6u;
     const uint32_t kd = std::max<uint32_t>(1u, std::min<uint32_t>(env_u32("SSW_PATCH_KD", kd_default), 32u));
     const uint32_t want_stages = std::max<uint32_t>(2u, std::min<uint32_t>(env_u32("SSW_PATCH_STAGES", 3), kMaxStages));
