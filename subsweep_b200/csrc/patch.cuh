@@ -85,7 +85,7 @@ struct __align__(16) PHdr {
     uint16_t kind;     // 0 tile, 1 head
     uint16_t n;        // tile: slots; head: upwind macro-tiles to wait for
     uint16_t a16;      // tile: entries; head: cells of the patch
-    uint16_t b16;      // tile: bit 0 = last tile of the macro-tile, bits 8.. = shuffle steps; head: direction group
+    uint16_t b16;      // tile: bit 0 = last tile of the macro-tile; head: direction group | directions in the group << 10
     uint32_t c32;      // tile: first slot of the tile inside the macro-tile; head: external entries
     uint32_t next_off16, next_bytes;   // packet that goes into this ring stage next (bytes = 0: none)
     uint32_t gslot0;   // head: first global slot of the macro-tile; tile: idx offset | lcell offset << 16 (16-B units)
@@ -119,15 +119,15 @@ __host__ __device__ inline PTileLayout ptile_layout(uint32_t n, uint32_t E) {
     return L;
 }
 
-struct PatchSmem { uint32_t bars, val, rec, acc, cellid, total; };
-__host__ __device__ inline PatchSmem patch_smem(uint32_t stages, uint32_t stage_bytes, uint32_t vmax, uint32_t pc_max) {
+struct PatchSmem { uint32_t bars, val, rec, inc, cellid, total; };
+__host__ __device__ inline PatchSmem patch_smem(uint32_t stages, uint32_t stage_bytes, uint32_t vmax, uint32_t pc_max, uint32_t smax) {
     PatchSmem L;
     uint32_t o = stages * stage_bytes;
     L.bars = o;   o += 8u * kMaxStages;
     L.val = o;    o += align16(8u * vmax);
     L.rec = o;    o += 16u * pc_max;
-    L.acc = o;    o += align16(8u * pc_max);
-    L.cellid = o; o += align16(4u * pc_max);
+    L.inc = o;    o += align16(8u * smax);   // incoming_total_rate per (patch cell, direction of the group)
+    L.cellid = o; o += 2u * align16(4u * pc_max);   // double-buffered: the flush of one macro-tile overlaps the next head
     L.total = o;
     return L;
 }
@@ -271,6 +271,8 @@ struct PFillArgs {
     const uint32_t *tile_rank;    // n_tiles
     const uint32_t *mt_slot0;     // n_mt + 1
     const uint32_t *mt_group, *mt_patch, *mt_ndep;   // n_mt
+    const uint16_t *group_rank;   // n_dl: index of the direction inside its group
+    const uint32_t *group_kd;     // G: directions in the group
     const uint64_t *head_off;     // n_mt: byte offset of the macro-tile's head packet in the stream
     const unsigned int *dep_tab;
     const uint32_t *rank_of;
@@ -281,7 +283,6 @@ struct PFillArgs {
 // one thread block per packet
 __global__ void __launch_bounds__(256)
 p_fill_kernel(PFillArgs a) {
-    __shared__ uint32_t s_maxlen;
     const PDesc d = a.ptab[blockIdx.x];
     const uint32_t blk = a.ptab_block[blockIdx.x];
     unsigned char *pkt = a.stream + a.stream_off[blk] + (size_t)d.off16 * 16u;
@@ -313,7 +314,7 @@ p_fill_kernel(PFillArgs a) {
         const uint32_t cell_pad = align16(4u * n_cells) / 4u;
         for (uint32_t i = tid; i < cell_pad; i += blockDim.x) cells[i] = i < n_cells ? a.pg.patch_cells[c0 + i] : 0u;
         if (tid == 0) {
-            h.kind = 1; h.n = (uint16_t)n_dep; h.a16 = (uint16_t)n_cells; h.b16 = (uint16_t)grp; h.c32 = n_ext;
+            h.kind = 1; h.n = (uint16_t)n_dep; h.a16 = (uint16_t)n_cells; h.b16 = (uint16_t)(grp | (a.group_kd[grp] << 10)); h.c32 = n_ext;
             h.gslot0 = mt0; h.n_slots = mt1 - mt0; h.rank = r;
             *reinterpret_cast<PHdr *>(pkt) = h;
         }
@@ -331,8 +332,6 @@ p_fill_kernel(PFillArgs a) {
     uint16_t *lcell = reinterpret_cast<uint16_t *>(pkt + L.lcell);
     uint32_t *info = reinterpret_cast<uint32_t *>(pkt + L.info);
     uint32_t *hext = reinterpret_cast<uint32_t *>(a.stream + a.head_off[r] + sizeof(PHdr) + align16(4u * a.mt_ndep[r]));
-    if (tid == 0) s_maxlen = 1;
-    __syncthreads();
     // zero the padding so the stream is fully initialised
     if (tid < 8) {
         if (tid == 0 && (E & 1u)) w[E] = 0.0;
@@ -348,7 +347,7 @@ p_fill_kernel(PFillArgs a) {
         const uint32_t k = a.k32[s];
         const uint32_t c = k / a.n_dl, dl = k - c * a.n_dl;
         const uint32_t pc = a.pg.patch_of[c];
-        lcell[tid] = a.pg.lidx[c];
+        lcell[tid] = (uint16_t)(a.pg.lidx[c] | ((uint32_t)a.group_rank[dl] << 10));
         const uint32_t e0 = (uint32_t)(a.upoff[s] - e_base);
         uint32_t e = e0, n_per = 0;
         uint32_t x = (uint32_t)(a.xoff[s] - a.xoff[mt0]);
@@ -383,21 +382,13 @@ p_fill_kernel(PFillArgs a) {
                 ++e;
             }
         }
-        const bool head = tid == 0 || a.k32[s - 1] / a.n_dl != c;
-        info[tid] = e0 | (min(n_per, 255u) << 16) | (head ? kInfoHead : 0u);
-        if (head) {
-            uint32_t len = 1;
-            while (tid + len < n && a.k32[s + len] / a.n_dl == c) ++len;
-            atomicMax(&s_maxlen, len);
-        }
+        info[tid] = e0 | (min(n_per, 255u) << 16);
     }
     __syncthreads();
     if (tid == 0) {
         info[n] = E;
-        uint32_t steps = 0;
-        while ((1u << steps) < min(s_maxlen, 32u)) ++steps;
         h.kind = 0; h.n = (uint16_t)n; h.a16 = (uint16_t)E;
-        h.b16 = (uint16_t)(((d.flags & kPLast) ? 1u : 0u) | (steps << 8));
+        h.b16 = (uint16_t)((d.flags & kPLast) ? 1u : 0u);
         h.c32 = slot0 - mt0;
         h.gslot0 = (L.idx >> 4) | ((L.lcell >> 4) << 16);   // tile packets: section offsets in 16-B units
         h.n_slots = L.info >> 4;
@@ -446,8 +437,9 @@ struct PatchArgs {
     const double2 *cellrec;   // {exp(-n_HI sigma size), source / D} per cell
     double *acc_cell;         // G x N
     double threshold;
-    uint32_t stages, stage_bytes, vmax, pc_max;
+    uint32_t stages, stage_bytes, vmax, pc_max, smax;
     uint32_t n_cells, epoch, poll_ns;
+    uint32_t exp;             // experiments only (SSW_PATCH_EXP): bit 0 no global store, bit 1 no rate reduction
     unsigned long long *prof; // optional per-block cycles {total, dependency poll, packet wait, packets}
 };
 
@@ -455,30 +447,29 @@ template <int THREADS, int MIN_BLOCKS, bool PROFILE>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 patch_sweep_kernel(PatchArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int WARPS = THREADS / 32;
-    __shared__ double s_wsum[2][WARPS];
-    __shared__ uint32_t s_wfirst[2][WARPS], s_wlast[2][WARPS];
     const uint32_t stages = a.stages, stage_bytes = a.stage_bytes;
-    const PatchSmem SL = patch_smem(stages, stage_bytes, a.vmax, a.pc_max);
+    const PatchSmem SL = patch_smem(stages, stage_bytes, a.vmax, a.pc_max, a.smax);
     unsigned char *const ring = smem;
     uint64_t *const full = reinterpret_cast<uint64_t *>(smem + SL.bars);
     double *const val = reinterpret_cast<double *>(smem + SL.val);
     double2 *const s_rec = reinterpret_cast<double2 *>(smem + SL.rec);
-    double *const s_acc = reinterpret_cast<double *>(smem + SL.acc);
-    uint32_t *const s_cellid = reinterpret_cast<uint32_t *>(smem + SL.cellid);
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    double *const s_inc = reinterpret_cast<double *>(smem + SL.inc);
+    uint32_t *s_cellid = reinterpret_cast<uint32_t *>(smem + SL.cellid);
+    const uint32_t cellid_stride = align16(4u * a.pc_max) / 4u;
+    uint32_t cellid_buf = 0;
+    const uint32_t tid = threadIdx.x;
     const uint32_t n_my = a.tab_off[blockIdx.x + 1] - a.tab_off[blockIdx.x];
     const unsigned char *const stream = a.stream + a.stream_off[blockIdx.x];
     double *const out_slot = a.out_slot;
     const double threshold = a.threshold;
     uint64_t policy = 0;
-    if (tid == 0) {
+    if (tid == THREADS - 32) {   // one thread issues every TMA copy: lane 0 of the last warp, the warp most often without slots
         for (uint32_t s = 0; s < stages; ++s) mbar_init(smem_u32(full + s), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         policy = policy_evict_first();
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == THREADS - 32) {
         const PDesc *tab = a.ptab + a.tab_off[blockIdx.x];
         const uint32_t pre = min(stages, n_my);
         for (uint32_t k = 0; k < pre; ++k) {
@@ -488,9 +479,9 @@ patch_sweep_kernel(PatchArgs a) {
                           smem_u32(full + k), policy);
         }
     }
-    uint32_t gslot0 = 0, n_slots = 0, group = 0, rank = 0, n_cells = 0;
+    uint32_t gslot0 = 0, n_slots = 0, group = 0, rank = 0, n_cells = 0, kdg = 1;
     uint32_t stage = 0, parity = 0;
-    long long t_begin = 0, t_poll = 0, t_pkt = 0, tp = 0;
+    long long t_begin = 0, t_poll = 0, t_pkt = 0, tp = 0, t_cmp = 0, t_scan = 0, t_bar = 0, t_post = 0, t_head = 0, tq = 0;
     if (PROFILE && tid == 0) t_begin = clock64();
     for (uint32_t k = 0; k < n_my; ++k) {
         if (PROFILE && tid == 0) tp = clock64();
@@ -498,20 +489,22 @@ patch_sweep_kernel(PatchArgs a) {
         if (PROFILE && tid == 0) t_pkt += clock64() - tp;
         unsigned char *const pkt = ring + (size_t)stage * stage_bytes;
         const PHdr h = *reinterpret_cast<const PHdr *>(pkt);
+        if (PROFILE && tid == 0) tq = clock64();
         if (h.kind) {
             // ---- macro-tile head: stage the patch's cell data, wait for the upwind macro-tiles, gather the
             //      fluxes that enter the patch
-            gslot0 = h.gslot0; n_slots = h.n_slots; rank = h.rank; group = h.b16; n_cells = h.a16;
+            gslot0 = h.gslot0; n_slots = h.n_slots; rank = h.rank; group = h.b16 & 0x3ffu; kdg = h.b16 >> 10; n_cells = h.a16;
             const uint32_t n_dep = h.n, n_ext = h.c32;
             const HeadLayout L = head_layout(n_dep, n_ext, n_cells);
             const uint32_t *const dep = reinterpret_cast<const uint32_t *>(pkt + L.dep);
             const uint32_t *const ext = reinterpret_cast<const uint32_t *>(pkt + L.ext);
             const uint32_t *const cells = reinterpret_cast<const uint32_t *>(pkt + L.cells);
+            cellid_buf ^= 1u;
+            s_cellid = reinterpret_cast<uint32_t *>(smem + SL.cellid) + cellid_buf * cellid_stride;
             for (uint32_t i = tid; i < n_cells; i += THREADS) {
                 const uint32_t c = cells[i];
                 s_cellid[i] = c;
                 s_rec[i] = __ldg(a.cellrec + c);
-                s_acc[i] = 0.0;
             }
             if (tid < n_dep) {
                 if (PROFILE && tid == 0) tp = clock64();
@@ -521,39 +514,36 @@ patch_sweep_kernel(PatchArgs a) {
             }
             __syncthreads();
             double *const vx = val + n_slots;
-            for (uint32_t i = tid; i < n_ext; i += 4u * THREADS) {
-                const uint32_t i1 = i + THREADS, i2 = i + 2u * THREADS, i3 = i + 3u * THREADS;
-                const bool p1 = i1 < n_ext, p2 = i2 < n_ext, p3 = i3 < n_ext;
-                double v0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-                v0 = __ldcg(out_slot + ext[i]);
-                if (p1) v1 = __ldcg(out_slot + ext[i1]);
-                if (p2) v2 = __ldcg(out_slot + ext[i2]);
-                if (p3) v3 = __ldcg(out_slot + ext[i3]);
-                vx[i] = v0;
-                if (p1) vx[i1] = v1;
-                if (p2) vx[i2] = v2;
-                if (p3) vx[i3] = v3;
+            for (uint32_t i = tid; i < n_ext; i += 8u * THREADS) {   // eight independent gathers in flight per thread
+                double v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t ij = i + (uint32_t)j * THREADS;
+                    v[j] = ij < n_ext ? __ldcg(out_slot + ext[ij]) : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t ij = i + (uint32_t)j * THREADS;
+                    if (ij < n_ext) vx[ij] = v[j];
+                }
             }
             __syncthreads();   // external values visible; every thread is done with the stage
-            if (tid == 0 && h.next_bytes) {
-                fence_proxy_async_smem();
+            if (tid == THREADS - 32 && h.next_bytes) {
                 mbar_expect_tx(smem_u32(full + stage), h.next_bytes);
                 tma_bulk_load(smem_u32(pkt), stream + (size_t)h.next_off16 * 16u, h.next_bytes, smem_u32(full + stage), policy);
             }
         } else {
             // ---- one tile: <= THREADS tasks of one sub-level; every value it reads is in shared memory
             const uint32_t n = h.n, lslot0 = h.c32;
-            const uint32_t scan_steps = h.b16 >> 8;
             const double *const w = reinterpret_cast<const double *>(pkt + sizeof(PHdr));
             const uint16_t *const idx = reinterpret_cast<const uint16_t *>(pkt + ((h.gslot0 & 0xffffu) << 4));
             const uint16_t *const lcell = reinterpret_cast<const uint16_t *>(pkt + ((h.gslot0 >> 16) << 4));
             const uint32_t *const info = reinterpret_cast<const uint32_t *>(pkt + (h.n_slots << 4));
-            uint32_t lc = 0xffffffffu, inf = 0;
-            double inc = 0.0;
-            if (tid < n) {
-                lc = lcell[tid];
-                inf = info[tid];
+            if (tid < n) {   // (warps beyond the tile's slots only keep the barrier)
+                const uint32_t lcj = lcell[tid];   // patch-local cell | index of the direction inside its group << 10
+                const uint32_t inf = info[tid];
                 const uint32_t e1 = info[tid + 1] & 0xffffu;
+                const uint32_t lc = lcj & 0x3ffu;
                 const double2 rec = s_rec[lc];
                 uint32_t e = inf & 0xffffu;
                 const uint32_t em = e1 - ((inf >> 16) & 0xffu);
@@ -561,79 +551,69 @@ patch_sweep_kernel(PatchArgs a) {
                 // product and sum rounded separately, Local faces in face order, then the periodic ones: the
                 // arithmetic of stream.cuh bit for bit.  Four entries per round: their loads are independent,
                 // only the additions form a chain.
-                for (; e < e1; e += 4u) {
+#pragma unroll 1
+                for (; e < em; e += 4u) {
                     uint32_t vi[4];
                     double wv[4], vv[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const bool ok = e + j < e1;
+                        const bool ok = e + j < em;
                         vi[j] = ok ? idx[e + j] : 0u;
                         wv[j] = ok ? w[e + j] : 0.0;
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) vv[j] = val[vi[j]];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const double pr = __dmul_rn(vv[j], wv[j]);
-                        if (e + j < em) in_loc = __dadd_rn(in_loc, pr);
-                        else if (e + j < e1) in_per = __dadd_rn(in_per, pr);
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        if (e + j < em) in_loc = __dadd_rn(in_loc, __dmul_rn(vv[j], wv[j]));
                 }
-                inc = in_loc;                                           // incoming_total_rate[d]
+#pragma unroll 1
+                for (uint32_t ep = em; ep < e1; ++ep) in_per = __dadd_rn(in_per, __dmul_rn(val[idx[ep]], w[ep]));
                 const double total = (in_loc + rec.y) + in_per;         // site.rs:49-56
                 // HydrogenOnly::get_outgoing_rate, hydrogen_only/mod.rs:81-87
                 const double out = (total < threshold) ? 0.0 : total * rec.x;
                 val[lslot0 + tid] = out;
-                __stcg(out_slot + gslot0 + lslot0 + tid, out);
+                if (!(a.exp & 1u)) __stcg(out_slot + gslot0 + lslot0 + tid, out);
+                s_inc[lc * kdg + (lcj >> 10)] = in_loc;                 // incoming_total_rate[d], summed per cell when the macro-tile is done
             }
-            // segmented suffix sums over the lanes of a warp (a segment = the directions of one cell)
-            const uint32_t stops = __ballot_sync(0xffffffffu, (inf & kInfoHead) != 0 || tid >= n);
-            const uint32_t rest = lane == 31u ? 0u : (stops >> (lane + 1u));
-            const uint32_t seg_end = rest ? lane + (uint32_t)__ffs((int)rest) : 32u;
-            double sum = inc;
-            for (uint32_t st = 0, o = 1; st < scan_steps; ++st, o <<= 1) {
-                const double v = __shfl_down_sync(0xffffffffu, sum, o);
-                if (lane + o < seg_end) sum += v;
-            }
-            const uint32_t lc_last = __shfl_sync(0xffffffffu, lc, 31);
-            const uint32_t buf = k & 1u;
-            if (lane == 0) {
-                s_wsum[buf][warp] = sum;
-                s_wfirst[buf][warp] = lc;
-                s_wlast[buf][warp] = lc_last;
-            }
+            if (PROFILE && tid == 0) { const long long t = clock64(); t_cmp += t - tq; tq = t; }
             __syncthreads();   // this sub-level's rates are visible; every thread is done with the stage
-            if (tid == 0 && h.next_bytes) {
-                fence_proxy_async_smem();
+            if (PROFILE && tid == 0) { const long long t = clock64(); t_bar += t - tq; tq = t; }
+            // the ring stage was only read (generic proxy), never written: no proxy fence before the refill
+            if (tid == THREADS - 32 && h.next_bytes) {
                 mbar_expect_tx(smem_u32(full + stage), h.next_bytes);
                 tma_bulk_load(smem_u32(pkt), stream + (size_t)h.next_off16 * 16u, h.next_bytes, smem_u32(full + stage), policy);
             }
-            if (inf & kInfoHead) {
-                if (lc_last == lc) {   // the segment runs on into the following warps
-                    for (uint32_t ww = warp + 1; ww < (uint32_t)WARPS && s_wfirst[buf][ww] == lc; ++ww) {
-                        sum += s_wsum[buf][ww];
-                        if (s_wlast[buf][ww] != lc) break;
-                    }
-                }
-                s_acc[lc] += sum;
-            }
             if (h.b16 & 1u) {
-                // ---- macro-tile done: store sum_d incoming of the group per cell, publish the done flag
-                __syncthreads();
-                double *const acc = a.acc_cell + (size_t)group * a.n_cells;
-                for (uint32_t i = tid; i < n_cells; i += THREADS) __stcg(acc + s_cellid[i], s_acc[i]);
-                __syncthreads();   // (the next head packet overwrites s_acc / s_cellid)
-                // every outgoing rate of the macro-tile was stored before the barriers above: the release is cumulative
+                // ---- macro-tile done.  Every outgoing rate of the macro-tile was stored before the barrier above, so the
+                //      done flag goes out first (the release is cumulative over the block's stores; downwind macro-tiles
+                //      are waiting for it).  Then sum_d incoming of the group's directions per cell, in direction order
+                //      (src/sweep/mod.rs:554-558): plain stores, every (group, cell) is written exactly once per sweep
                 if (tid == 0) st_release_gpu(a.mt_flag + rank, a.epoch);
+                double *const acc = a.acc_cell + (size_t)group * a.n_cells;
+                for (uint32_t i = tid; i < n_cells; i += THREADS) {
+                    const double *const row = s_inc + i * kdg;
+                    double sum = 0.0;
+                    for (uint32_t j = 0; j < kdg; ++j) sum += row[j];
+                    __stcg(acc + s_cellid[i], sum);
+                }
+                // no barrier: the next head fills the other s_cellid buffer, and two barriers separate it from the
+                // next write to s_inc
             }
         }
+        if (PROFILE && tid == 0) { if (h.kind) t_head += clock64() - tq; else t_post += clock64() - tq; }
         if (++stage == stages) { stage = 0; parity ^= 1u; }
     }
     if (PROFILE && tid == 0) {
-        a.prof[4 * blockIdx.x + 0] = (unsigned long long)(clock64() - t_begin);
-        a.prof[4 * blockIdx.x + 1] = (unsigned long long)t_poll;
-        a.prof[4 * blockIdx.x + 2] = (unsigned long long)t_pkt;
-        a.prof[4 * blockIdx.x + 3] = n_my;
+        a.prof[10 * blockIdx.x + 0] = (unsigned long long)(clock64() - t_begin);
+        a.prof[10 * blockIdx.x + 1] = (unsigned long long)t_poll;
+        a.prof[10 * blockIdx.x + 2] = (unsigned long long)t_pkt;
+        a.prof[10 * blockIdx.x + 3] = n_my;
+        a.prof[10 * blockIdx.x + 4] = (unsigned long long)t_cmp;
+        a.prof[10 * blockIdx.x + 5] = (unsigned long long)t_scan;
+        a.prof[10 * blockIdx.x + 6] = (unsigned long long)t_bar;
+        a.prof[10 * blockIdx.x + 7] = (unsigned long long)t_post;
+        a.prof[10 * blockIdx.x + 8] = (unsigned long long)t_head;
     }
 }
 
@@ -663,8 +643,11 @@ struct DTmp {
 };
 
 // direction groups: directions of one octant (sign pattern of the direction vector), at most kd per group
-inline uint32_t make_direction_groups(const double *dirs_local, uint32_t n_dl, uint32_t kd, std::vector<uint16_t> &group_of) {
+inline uint32_t make_direction_groups(const double *dirs_local, uint32_t n_dl, uint32_t kd, std::vector<uint16_t> &group_of,
+                                      std::vector<uint16_t> &group_rank, std::vector<uint32_t> &group_kd) {
     group_of.assign(n_dl, 0);
+    group_rank.assign(n_dl, 0);
+    group_kd.clear();
     std::vector<std::vector<uint32_t>> cls(27);
     for (uint32_t dl = 0; dl < n_dl; ++dl) {
         int code = 0;
@@ -678,7 +661,12 @@ inline uint32_t make_direction_groups(const double *dirs_local, uint32_t n_dl, u
     for (auto &c : cls) {
         if (c.empty()) continue;
         const uint32_t chunks = ((uint32_t)c.size() + kd - 1) / kd;
-        for (uint32_t i = 0; i < c.size(); ++i) group_of[c[i]] = (uint16_t)(G + (uint32_t)((uint64_t)i * chunks / c.size()));
+        group_kd.resize(G + chunks, 0);
+        for (uint32_t i = 0; i < c.size(); ++i) {
+            const uint32_t grp = G + (uint32_t)((uint64_t)i * chunks / c.size());
+            group_of[c[i]] = (uint16_t)grp;
+            group_rank[c[i]] = (uint16_t)group_kd[grp]++;   // c is ascending in dl: rank = direction order inside the group
+        }
         G += chunks;
     }
     return G;
@@ -704,10 +692,14 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
     uint64_t launches = 0;
     try {
         // 1. direction groups, wavefront level of every task, quotient graph
-        std::vector<uint16_t> group_of;
-        const uint32_t G = make_direction_groups(dirs_local, n_dl, kd, group_of);
+        std::vector<uint16_t> group_of, group_rank;
+        std::vector<uint32_t> group_kd;
+        const uint32_t G = make_direction_groups(dirs_local, n_dl, kd, group_of, group_rank, group_kd);
         if ((uint64_t)G * P > kMaxRank) throw PatchUnsupported("more than 2^20 macro-tiles");
+        if (G > 1023) throw PatchUnsupported("more than 1023 direction groups");
         DTmp<uint16_t> group_dev;  group_dev.upload(group_of, stream, "group_of");
+        DTmp<uint16_t> group_rank_dev; group_rank_dev.upload(group_rank, stream, "group_rank");
+        DTmp<uint32_t> group_kd_dev;   group_kd_dev.upload(group_kd, stream, "group_kd");
         DTmp<uint32_t> tlevel;     tlevel.alloc(n, "tlevel");
         DTmp<unsigned int> minlev; minlev.alloc((size_t)P * n_dl, "minlev");
         DTmp<unsigned int> dep_tab; dep_tab.alloc((size_t)G * P * kMaxPatchDeps, "dep_tab");
@@ -920,13 +912,16 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
             mt_tile0[n_mt] = t;
             if (t != n_tiles) throw std::runtime_error("compile_patch_schedule: tiles out of rank order");
         }
-        uint32_t max_bytes = 0, vmax = 0, pc_max = 0;
+        uint32_t max_bytes = 0, vmax = 0, pc_max = 0, smax = 0;
         std::vector<uint32_t> head_bytes(n_mt), tile_bytes(n_tiles);
         for (uint32_t r = 0; r < n_mt; ++r) {
             const uint64_t n_ext = mtx[r + 1] - mtx[r];
             const uint64_t ns = mt_slot0_h[r + 1] - mt_slot0_h[r];
             if (ns + n_ext > 65535ull) throw PatchUnsupported("a macro-tile holds more than 65535 values (smaller patches or direction groups needed)");
             vmax = std::max<uint32_t>(vmax, (uint32_t)(ns + n_ext));
+            smax = std::max<uint32_t>(smax, (uint32_t)ns);
+            if (ns != (uint64_t)patch_size[mt_patch[r]] * group_kd[mt_group[r]])
+                throw std::runtime_error("compile_patch_schedule: macro-tile is not (patch cells) x (group directions)");
             pc_max = std::max(pc_max, patch_size[mt_patch[r]]);
             head_bytes[r] = head_layout(mt_ndep[r], (uint32_t)n_ext, patch_size[mt_patch[r]]).bytes;
             max_bytes = std::max(max_bytes, head_bytes[r]);
@@ -941,9 +936,9 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
         const uint32_t stage_bytes = std::max<uint32_t>(128u, (max_bytes + 127u) & ~127u);
         PatchKernel kernel = patch_kernel_for(threads, false);
         uint32_t stages = want_stages;
-        size_t smem = patch_smem(stages, stage_bytes, vmax, pc_max).total;
+        size_t smem = patch_smem(stages, stage_bytes, vmax, pc_max, smax).total;
         const size_t smem_block_max = 227u * 1024u - 1024u;
-        while (smem > smem_block_max && stages > 2) { --stages; smem = patch_smem(stages, stage_bytes, vmax, pc_max).total; }
+        while (smem > smem_block_max && stages > 2) { --stages; smem = patch_smem(stages, stage_bytes, vmax, pc_max, smax).total; }
         if (smem > smem_block_max) throw PatchUnsupported("a macro-tile does not fit in shared memory");
         cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "set max dynamic smem");
         int per_sm = 0;
@@ -1014,6 +1009,7 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
         fa.ptab = C.ptab; fa.ptab_block = ptab_block_dev.p; fa.tab_off = C.tab_off; fa.stream_off = C.stream_off;
         fa.stream = C.stream; fa.tile_start = tile_start.p; fa.tile_rank = tile_rank_dev.p; fa.mt_slot0 = mt_slot0.p;
         fa.mt_group = mt_group_dev.p; fa.mt_patch = mt_patch_dev.p; fa.mt_ndep = mt_ndep_dev.p; fa.head_off = head_off_dev.p;
+        fa.group_rank = group_rank_dev.p; fa.group_kd = group_kd_dev.p;
         fa.dep_tab = dep_tab.p; fa.rank_of = rank_dev.p; fa.lag_src = C.lag_src; fa.counters = counters.p;
         if (n_packets) p_fill_kernel<<<n_packets, 256, 0, stream>>>(fa);
         s_convert_state_kernel<<<blocks_n, 256, 0, stream>>>(k32.p, n, N, n_dl, q_nat, C.ttot_slot, C.out_slot);
@@ -1033,6 +1029,7 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
         C.n_mt = n_mt;
         C.vmax = vmax;
         C.pc_max = pc_max;
+        C.smax = smax;
         C.kd = kd;
         C.n_patches = P;
         C.patch_levels = max_level + 1;
@@ -1074,14 +1071,16 @@ inline void run_patch(Compiled &C, const GridView &g, const uint32_t *pcells, co
     a.stage_bytes = C.stage_bytes;
     a.vmax = C.vmax;
     a.pc_max = C.pc_max;
+    a.smax = C.smax;
     a.n_cells = C.n_cells;
     a.epoch = ++C.epoch;
     a.poll_ns = env_u32("SSW_STREAM_POLL_NS", 20);
+    a.exp = env_u32("SSW_PATCH_EXP", 0);
     a.prof = nullptr;
     unsigned long long *prof_dev = nullptr;
     if (env_u32("SSW_STREAM_PROFILE", 0)) {
-        cuda_ok(cudaMalloc(&prof_dev, sizeof(unsigned long long) * 4 * (size_t)C.n_blocks), "malloc prof");
-        cuda_ok(cudaMemsetAsync(prof_dev, 0, sizeof(unsigned long long) * 4 * (size_t)C.n_blocks, stream), "memset prof");
+        cuda_ok(cudaMalloc(&prof_dev, sizeof(unsigned long long) * 10 * (size_t)C.n_blocks), "malloc prof");
+        cuda_ok(cudaMemsetAsync(prof_dev, 0, sizeof(unsigned long long) * 10 * (size_t)C.n_blocks, stream), "memset prof");
         a.prof = prof_dev;
     }
     uint64_t launches = 1;
@@ -1090,7 +1089,7 @@ inline void run_patch(Compiled &C, const GridView &g, const uint32_t *pcells, co
         ++launches;
     }
     PatchKernel kernel = patch_kernel_for(C.threads, prof_dev != nullptr);
-    const size_t smem = patch_smem(C.stages, C.stage_bytes, C.vmax, C.pc_max).total;
+    const size_t smem = patch_smem(C.stages, C.stage_bytes, C.vmax, C.pc_max, C.smax).total;
     cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "set max dynamic smem");
     void *args[] = {&a};
     // cooperative launch only to guarantee co-residency of all blocks (the done flags are polled)
@@ -1103,15 +1102,20 @@ inline void run_patch(Compiled &C, const GridView &g, const uint32_t *pcells, co
         ++launches;
     }
     if (prof_dev) {
-        std::vector<unsigned long long> h(4 * (size_t)C.n_blocks);
+        std::vector<unsigned long long> h(10 * (size_t)C.n_blocks);
         cudaMemcpyAsync(h.data(), prof_dev, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, stream);
         cudaStreamSynchronize(stream);
         cudaFree(prof_dev);
-        double tot = 0, poll = 0, pkt = 0, packets = 0, tmax = 0;
+        double tot = 0, poll = 0, pkt = 0, packets = 0, tmax = 0, cmp = 0, scan = 0, bar = 0, post = 0, head = 0;
         for (uint32_t b = 0; b < C.n_blocks; ++b) {
-            tot += (double)h[4 * b]; poll += (double)h[4 * b + 1]; pkt += (double)h[4 * b + 2]; packets += (double)h[4 * b + 3];
-            tmax = std::max(tmax, (double)h[4 * b]);
+            tot += (double)h[10 * b]; poll += (double)h[10 * b + 1]; pkt += (double)h[10 * b + 2]; packets += (double)h[10 * b + 3];
+            cmp += (double)h[10 * b + 4]; scan += (double)h[10 * b + 5]; bar += (double)h[10 * b + 6]; post += (double)h[10 * b + 7];
+            head += (double)h[10 * b + 8];
+            tmax = std::max(tmax, (double)h[10 * b]);
         }
+        fprintf(stderr, "[patch phases] thread 0, cycles per tile: compute %.0f  (unused %.0f)  barrier %.0f  post %.0f  mbar wait (all packets) %.0f;  "
+                        "cycles per head (incl. poll) %.0f\n",
+                cmp / C.n_tiles, scan / C.n_tiles, bar / C.n_tiles, post / C.n_tiles, pkt / packets, head / C.n_mt);
         fprintf(stderr, "[patch profile] blocks %u (%u/SM x %u thr) macro-tiles %u tiles %u  cycles/block mean %.0f max %.0f  "
                         "dependency poll %.1f%%  packet wait %.1f%%  cycles per packet %.0f  patch levels %u  vmax %u stage %u B x %u\n",
                 C.n_blocks, C.bps, C.threads, C.n_mt, C.n_tiles, tot / C.n_blocks, tmax, 100.0 * poll / tot, 100.0 * pkt / tot,

@@ -137,7 +137,7 @@ struct Compiled {
     // patch-ordered form (patch.cuh): macro-tiles (patch, direction group) with point-to-point done flags
     bool patch_mode = false;
     uint32_t n_groups_per = 1;      // rows of acc_per
-    uint32_t n_mt = 0, vmax = 0, pc_max = 0, epoch = 0;
+    uint32_t n_mt = 0, vmax = 0, pc_max = 0, smax = 0, epoch = 0;
     uint32_t kd = 0, n_patches = 0, patch_levels = 0;
     unsigned int *mt_flag = nullptr;   // n_mt: epoch of the sweep that last completed the macro-tile
     PDesc *ptab = nullptr;             // packet table, block-major

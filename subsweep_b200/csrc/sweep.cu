@@ -738,7 +738,14 @@ void Sweep::single_sweep(int cur) {
             const size_t t_sched = tic(T_SCHED);
             try {
                 bool patched = false;
-                if (have_patches && !(P.flags & SSW_FLAG_NO_PATCH_PATH) && stream_env_u32("SSW_PATCH", 1)) {
+                // Which compiled form?  The patch-ordered dataflow has the shorter critical path (46 instead of 382
+                // dependent steps at 128^3) and wins when the sweep is latency-bound: few local directions, i.e. a
+                // direction shard of a multi-GPU job.  With many directions the level-barrier stream keeps all SMs
+                // busy and has the higher throughput.  SSW_PATCH = 0 / 1 forces the choice.
+                const uint32_t patch_mode = stream_env_u32("SSW_PATCH", 2);
+                const bool want_patch = patch_mode == 1 || (patch_mode == 2 && (uint32_t)Dl <= stream_env_u32("SSW_PATCH_MAX_DIRS", 24));
+                if (!want_patch && have_patches) patch_note = "level-barrier stream preferred for this many local directions";
+                if (have_patches && !(P.flags & SSW_FLAG_NO_PATCH_PATH) && want_patch) {
                     try {
                         compile_patch_schedule(S.compiled, grid_view(), patch_view(), dirs_all.data() + 3 * (size_t)d0,
                                                S.tasks.p, S.level_off.p, S.n_tasks, S.n_levels, Dl, n_periodic, q.p,

@@ -48,8 +48,9 @@ def test_wavefront_levels_closed_form(cuda_lib, box):
     s.close()
 
 
-def test_compiled_and_generic_paths_agree_at_full_size(cuda_lib, box):
+def test_compiled_and_generic_paths_agree_at_full_size(cuda_lib, box, monkeypatch):
     params, g, f = box
+    monkeypatch.setenv("SSW_PATCH", "1")   # 84 directions would default to the level-barrier stream
     results = {}
     for name, flags in (("compiled", 0), ("stream", capi.FLAG_NO_PATCH_PATH), ("generic", capi.FLAG_NO_COMPILED_PATH)):
         s = Sweep(params, g, **f, flags=flags)

@@ -5,7 +5,7 @@ OUT=gpurun_out; mkdir -p $OUT
 LOG=$OUT/tune_patch.jsonl
 : > $LOG
 if [ "${RUN_TESTS:-0}" = "1" ]; then
-  timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 | tee $OUT/tune_patch_tests.log
+  timeout 1200 python -m pytest ${TESTS:-tests} -m gpu -q -x 2>&1 | tail -8 | tee $OUT/tune_patch_tests.log
 fi
 while read -r pc kd th st sh; do
   [ -z "${pc:-}" ] && continue
