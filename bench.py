@@ -285,7 +285,7 @@ def run_b200(args) -> None:
     import torch
     import torch.distributed as dist
     from subsweep_b200 import Sweep, build as libbuild
-    from subsweep_b200.distributed import init_from_env, make_allreduce
+    from subsweep_b200.distributed import init_from_env, make_allreduce, make_collectives
 
     rank, world, local_rank = init_from_env()
     if world != args.gpus and world > 1:
@@ -301,6 +301,7 @@ def run_b200(args) -> None:
 
     params, g, fields = build_workload(args.n, args.grid, args.dirs, args.levels, args.workload)
     allreduce = make_allreduce(device) if world > 1 else None
+    collectives = make_collectives(device) if world > 1 and not os.environ.get("SSW_BENCH_REPLICATED_CHEMISTRY") else None
     shard_rank, shard_world = rank, world
     if args.emulate_shard and world == 1:
         # profiling aid: one GPU runs rank 0's direction shard of a W-rank job with a no-op all-reduce, to tune the
@@ -308,7 +309,8 @@ def run_b200(args) -> None:
         shard_rank, shard_world = 0, args.emulate_shard
         allreduce = lambda ptr, n, stream: None   # noqa: E731
         args.no_e2e = True
-    sweep = Sweep(params, g, **fields, device_id=local_rank, rank=shard_rank, world_size=shard_world, allreduce=allreduce)
+    sweep = Sweep(params, g, **fields, device_id=local_rank, rank=shard_rank, world_size=shard_world, allreduce=allreduce,
+                  collectives=collectives)
     N = g.n_cells
     b_alg, f_up = algorithmic_bytes_per_update(g, sweep.directions.xyz)
 

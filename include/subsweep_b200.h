@@ -68,8 +68,12 @@ typedef struct ssw_params {
 enum {
     SSW_FLAG_NO_SCHEDULE_CACHE = 1u << 0, /* rebuild wavefront level sets every single sweep      */
     SSW_FLAG_NO_COMPILED_PATH = 1u << 1,  /* replay cached level sets from the generic task list   */
-    SSW_FLAG_NO_PATCH_PATH = 1u << 2      /* keep the level-barrier stream even when cell positions */
+    SSW_FLAG_NO_PATCH_PATH = 1u << 2,     /* keep the level-barrier stream even when cell positions */
                                           /* are known (ssw_set_cell_positions)                     */
+    SSW_FLAG_SHARED_DEVICE = 1u << 3      /* several handles of ONE process take turns on one device */
+                                          /* (tests that emulate ranks with threads): re-bind the    */
+                                          /* per-process direction table after every hook call.  The */
+                                          /* handles must never run concurrently.                    */
 };
 
 /* Flat (CSR) form of the per-particle `Cell` component (src/sweep/grid/cell.rs:92-133):
@@ -114,6 +118,18 @@ typedef enum ssw_field {
  * on either side.  Replaces the MPI flux messages of src/sweep/communicator.rs:59-95. */
 typedef int (*ssw_allreduce_fn)(void *ctx, double *buf, uint64_t n, void *cuda_stream);
 
+/* Optional second hook: reduce-scatter and all-gather, in place, with NCCL's in-place layout.  `buf` holds
+ * world_size chunks of n_per_rank doubles (DEVICE pointer, stream-ordered like ssw_allreduce_fn):
+ *   SSW_COLL_REDUCE_SCATTER  chunk `rank` of buf <- sum over ranks of their chunk `rank`
+ *                            (ncclReduceScatter(buf, buf + rank * n, n, ncclDouble, ncclSum, ...))
+ *   SSW_COLL_ALL_GATHER      every chunk r of buf <- chunk r of rank r's buf
+ *                            (ncclAllGather(buf + rank * n, buf, n, ncclDouble, ...))
+ * With it the chemistry after an all-cells sweep is sliced by cells instead of replicated on every rank
+ * (reduce-scatter of the rates, update of the own slice, all-gather of x / T / timescales); without it the
+ * all-reduce hook alone is used.  Sweeps over partial active sets always use the all-reduce. */
+enum { SSW_COLL_REDUCE_SCATTER = 1, SSW_COLL_ALL_GATHER = 2 };
+typedef int (*ssw_collective_fn)(void *ctx, int op, double *buf, uint64_t n_per_rank, void *cuda_stream);
+
 /* -- life cycle ------------------------------------------------------------------------- */
 
 /* Sweep::new (src/sweep/mod.rs:194-232) + init_sweep_system (:634-692).  Copies the grid and
@@ -124,6 +140,7 @@ int ssw_create(const ssw_params *params, const ssw_grid *grid, const double *den
 /* Drop (src/sweep/communicator.rs:116-125). */
 void ssw_destroy(ssw_handle *h);
 int ssw_set_allreduce(ssw_handle *h, ssw_allreduce_fn fn, void *ctx);
+int ssw_set_collectives(ssw_handle *h, ssw_collective_fn fn, void *ctx);
 /* Optional, once, before the first ssw_run_sweeps: the `Position` component of every cell
  * (src/components.rs, N x 3, cell order).  The solver itself never needs positions
  * (Sweep::new does not take them, src/sweep/mod.rs:194-232); they let the library group cells into

@@ -14,7 +14,7 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "libsubsweep_b200.so"
 
 SSW_OK, SSW_E_INVALID, SSW_E_CUDA, SSW_E_DEADLOCK, SSW_E_NOMEM, SSW_E_COMM = 0, -1, -2, -3, -4, -5
 FACE_LOCAL, FACE_BOUNDARY, FACE_LOCAL_PERIODIC = 0, 1, 2
-FLAG_NO_SCHEDULE_CACHE, FLAG_NO_COMPILED_PATH, FLAG_NO_PATCH_PATH = 1, 2, 4
+FLAG_NO_SCHEDULE_CACHE, FLAG_NO_COMPILED_PATH, FLAG_NO_PATCH_PATH, FLAG_SHARED_DEVICE = 1, 2, 4, 8
 
 FIELDS = {
     "ionized_hydrogen_fraction": 0, "temperature": 1, "timestep": 2, "photon_rate": 3,
@@ -76,6 +76,8 @@ class TimeSeries(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)
+COLLECTIVE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p)
+COLL_REDUCE_SCATTER, COLL_ALL_GATHER = 1, 2
 
 # every symbol include/subsweep_b200.h declares: name -> (restype, argtypes)
 H = C.c_void_p
@@ -83,6 +85,7 @@ SYMBOLS = {
     "ssw_create": (C.c_int, [C.POINTER(Params), C.POINTER(Grid), c_double_p, c_double_p, c_double_p, c_double_p, C.POINTER(H)]),
     "ssw_destroy": (None, [H]),
     "ssw_set_allreduce": (C.c_int, [H, ALLREDUCE_FN, C.c_void_p]),
+    "ssw_set_collectives": (C.c_int, [H, COLLECTIVE_FN, C.c_void_p]),
     "ssw_set_cell_positions": (C.c_int, [H, c_double_p]),
     "ssw_patch_note": (C.c_char_p, [H]),
     "ssw_run_sweeps": (C.c_int, [H, c_double_p]),

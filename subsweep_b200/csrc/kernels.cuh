@@ -629,12 +629,12 @@ struct ChemStats {
 
 __global__ void __launch_bounds__(128)
 chemistry_kernel(CellView cv, const uint32_t *__restrict__ act_list, uint32_t n_act,
-                 const double *__restrict__ rate_act, ChemParams cp, ChemStats *stats) {
+                 const double *__restrict__ rate_act, ChemParams cp, ChemStats *stats, uint32_t first_cell) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long attempts = 0;
     unsigned int depth = 0, failed = 0;
     if (k < n_act) {
-        const uint32_t c = act_list ? act_list[k] : k;
+        const uint32_t c = act_list ? act_list[k] : first_cell + k;   // no list: the contiguous cells [first_cell, first_cell + n_act)
         const double rate = rate_act[k];
         const int lvl = cv.level[c];
         const double timestep = cp.max_timestep * exp2(-(double)lvl);  // max_timestep * 0.5^level (exact)
@@ -691,6 +691,39 @@ chemistry_kernel(CellView cv, const uint32_t *__restrict__ act_list, uint32_t n_
         atomicAdd(&stats->cells, (unsigned long long)n_here);
         atomicMax(&stats->max_depth, s_depth);
     }
+}
+
+// Cell-sliced chemistry of a direction-sharded job: every rank updates the cells
+// [rank * n_per, (rank + 1) * n_per) and packs what the other ranks need -- x, T, change_timescale, timestep and
+// the all-reduced rate (= previous_incoming_total_rate) -- into its chunk of the all-gather buffer
+// pack[rank][field][k]; after the all-gather every rank unpacks the other ranks' chunks.
+constexpr int kPackFields = 5;
+__global__ void __launch_bounds__(256)
+chem_pack_kernel(CellView cv, uint32_t first_cell, uint32_t n_own, uint32_t n_per, double *__restrict__ chunk) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_own) return;
+    const uint32_t c = first_cell + k;
+    chunk[k] = cv.x[c];
+    chunk[(size_t)n_per + k] = cv.T[c];
+    chunk[2 * (size_t)n_per + k] = cv.tau[c];
+    chunk[3 * (size_t)n_per + k] = cv.ts[c];
+    chunk[4 * (size_t)n_per + k] = cv.prev_rate[c];
+}
+
+__global__ void __launch_bounds__(256)
+chem_unpack_kernel(CellView cv, uint32_t n_cells, uint32_t n_per, uint32_t my_rank, const double *__restrict__ pack) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const uint32_t r = c / n_per, k = c - r * n_per;
+    if (r == my_rank) return;
+    const double *chunk = pack + (size_t)r * kPackFields * n_per;
+    const double x = chunk[k];
+    cv.x[c] = x;
+    cv.T[c] = chunk[(size_t)n_per + k];
+    cv.tau[c] = chunk[2 * (size_t)n_per + k];
+    cv.ts[c] = chunk[3 * (size_t)n_per + k];
+    cv.prev_rate[c] = chunk[4 * (size_t)n_per + k];
+    cv.att[c] = non_absorbed_fraction(cv.rho[c], x, cv.size[c]);
 }
 
 // att = exp(-n_HI sigma size) for all cells (create / set_inputs)

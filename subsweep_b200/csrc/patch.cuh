@@ -685,7 +685,7 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
     const uint32_t n = (uint32_t)n_tasks, n_dl = (uint32_t)n_local_dirs, N = g.n_cells, P = pg.n_patches;
     const uint32_t threads_env = env_u32("SSW_PATCH_THREADS", 128);
     const uint32_t threads = threads_env == 256 ? 256u : (threads_env == 64 ? 64u : 128u);
-    const uint32_t kd_default = n_dl <= 24 ? 3u : 6u;
+    const uint32_t kd_default = n_dl <= 24 ? 3u : 11u;   // many directions: one group per octant (10-11 of the 84)
     const uint32_t kd = std::max<uint32_t>(1u, std::min<uint32_t>(env_u32("SSW_PATCH_KD", kd_default), 32u));
     const uint32_t want_stages = std::max<uint32_t>(2u, std::min<uint32_t>(env_u32("SSW_PATCH_STAGES", 3), kMaxStages));
     const unsigned blocks_n = (unsigned)((n + 255) / 256);

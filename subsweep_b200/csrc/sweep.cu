@@ -168,6 +168,9 @@ struct Sweep {
 
     ssw_allreduce_fn allreduce = nullptr;
     void *allreduce_ctx = nullptr;
+    ssw_collective_fn collective = nullptr;   // optional: reduce-scatter / all-gather -> cell-sliced chemistry
+    void *collective_ctx = nullptr;
+    DevBuf<double> chem_pack;                 // world_size x kPackFields x cells_per_rank
 
     // statistics / timers
     uint64_t stat[16] = {0};
@@ -307,6 +310,8 @@ struct Sweep {
     void read_field(int field, double *out);
     void all_rates(double *dev_out);
     void maybe_allreduce(double *buf, uint64_t n);
+    uint32_t cells_per_rank() const { return (uint32_t)(((uint64_t)N + P.world_size - 1) / P.world_size); }
+    void run_collective(int op, double *buf, uint64_t n_per_rank);
 };
 
 static int coop_grid(const void *kernel, int threads, int num_sms) {
@@ -437,7 +442,8 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     ctl.alloc(1);
     flags.alloc(N);
     n_selected.alloc(1);
-    rate_act.alloc(N);
+    rate_act.alloc((size_t)cells_per_rank() * P.world_size);   // >= N: padded to whole per-rank chunks (reduce-scatter)
+    rate_act.zero(stream);
     cellrec.alloc(N);
     cell_tmp.alloc(N);
     cell_tmp2.alloc(N);
@@ -483,7 +489,10 @@ void Sweep::set_positions(const double *xyz) {
     double vol = 1.0;
     for (int k = 0; k < 3; ++k)
         if (hi[k] > lo[k]) { ++dims; vol *= hi[k] - lo[k]; }
-    double target = (double)stream_env_u32("SSW_PATCH_CELLS", 512);
+    // patch size: a direction shard (few local directions) is bound by the chain of dependent macro-tiles -> large
+    // patches (8^3), few levels; with many directions the sweep is throughput-bound and small patches (4^3) keep far
+    // more macro-tiles resident per SM (measured on B200)
+    double target = (double)stream_env_u32("SSW_PATCH_CELLS", Dl <= 24 ? 512 : 64);
     target = std::min<double>(std::max<double>(target, 8.0), (double)kMaxPatchCells);
     std::vector<uint32_t> pof(N), poff, pcl(N);
     std::vector<uint16_t> lidx(N);
@@ -671,6 +680,14 @@ void Sweep::maybe_allreduce(double *buf, uint64_t n) {
     const size_t t = tic(T_ALLREDUCE);
     // stream-ordered: the hook enqueues the collective behind the work already queued on `stream`
     if (allreduce(allreduce_ctx, buf, n, (void *)stream) != 0) fail(SSW_E_COMM, "all-reduce hook failed");
+    if (P.flags & SSW_FLAG_SHARED_DEVICE) bind();   // another handle of this process may have run inside the hook
+    toc(t);
+}
+
+void Sweep::run_collective(int op, double *buf, uint64_t n_per_rank) {
+    const size_t t = tic(T_ALLREDUCE);
+    if (collective(collective_ctx, op, buf, n_per_rank, (void *)stream) != 0) fail(SSW_E_COMM, "collective hook failed (op %d)", op);
+    if (P.flags & SSW_FLAG_SHARED_DEVICE) bind();
     toc(t);
 }
 
@@ -738,13 +755,11 @@ void Sweep::single_sweep(int cur) {
             const size_t t_sched = tic(T_SCHED);
             try {
                 bool patched = false;
-                // Which compiled form?  The patch-ordered dataflow has the shorter critical path (46 instead of 382
-                // dependent steps at 128^3) and wins when the sweep is latency-bound: few local directions, i.e. a
-                // direction shard of a multi-GPU job.  With many directions the level-barrier stream keeps all SMs
-                // busy and has the higher throughput.  SSW_PATCH = 0 / 1 forces the choice.
-                const uint32_t patch_mode = stream_env_u32("SSW_PATCH", 2);
-                const bool want_patch = patch_mode == 1 || (patch_mode == 2 && (uint32_t)Dl <= stream_env_u32("SSW_PATCH_MAX_DIRS", 24));
-                if (!want_patch && have_patches) patch_note = "level-barrier stream preferred for this many local directions";
+                // Which compiled form?  The patch-ordered dataflow (no device-wide barriers, 46 instead of 382 dependent
+                // steps at 128^3) whenever cell positions are known and the grid admits it; else the level-barrier
+                // stream.  SSW_PATCH=0 switches the patch form off.
+                const bool want_patch = stream_env_u32("SSW_PATCH", 1) != 0;
+                if (!want_patch && have_patches) patch_note = "patch form switched off (SSW_PATCH=0)";
                 if (have_patches && !(P.flags & SSW_FLAG_NO_PATCH_PATH) && want_patch) {
                     try {
                         compile_patch_schedule(S.compiled, grid_view(), patch_view(), dirs_all.data() + 3 * (size_t)d0,
@@ -846,15 +861,34 @@ void Sweep::single_sweep(int cur) {
                                                               n_periodic, rate_act.p);
     }
     launched();
-    maybe_allreduce(rate_act.p, n_act);
     ChemParams cp;
     cp.max_timestep = P.max_timestep_s;
     cp.threshold = P.significant_rate_threshold_per_s;
     cp.scale_factor = P.scale_factor;
     cp.safety = P.chemistry_timestep_safety_factor;
     cp.prevent_cooling = P.prevent_cooling;
-    chemistry_kernel<<<cdiv(n_act, 128), 128, 0, stream>>>(cell_view(), act, n_act, rate_act.p, cp, chem_stats.p);
-    launched();
+    if (all && P.world_size > 1 && collective) {
+        // all cells active on W ranks: reduce-scatter the partial rates, update the own slice of cells, all-gather
+        // the results -- the chemistry is not replicated W times, and every rank ends with bit-identical state
+        const uint32_t n_per = cells_per_rank();
+        const uint32_t first = std::min<uint64_t>((uint64_t)P.rank * n_per, N);
+        const uint32_t n_own = std::min<uint32_t>(n_per, N - first);
+        chem_pack.ensure((size_t)P.world_size * kPackFields * n_per);
+        run_collective(SSW_COLL_REDUCE_SCATTER, rate_act.p, n_per);
+        double *chunk = chem_pack.p + (size_t)P.rank * kPackFields * n_per;
+        if (n_own) {
+            chemistry_kernel<<<cdiv(n_own, 128), 128, 0, stream>>>(cell_view(), nullptr, n_own, rate_act.p + first, cp, chem_stats.p, first);
+            chem_pack_kernel<<<cdiv(n_own, 256), 256, 0, stream>>>(cell_view(), first, n_own, n_per, chunk);
+            launched(2);
+        }
+        run_collective(SSW_COLL_ALL_GATHER, chem_pack.p, (uint64_t)kPackFields * n_per);
+        chem_unpack_kernel<<<cdiv(N, 256), 256, 0, stream>>>(cell_view(), N, n_per, (uint32_t)P.rank, chem_pack.p);
+        launched();
+    } else {
+        maybe_allreduce(rate_act.p, n_act);
+        chemistry_kernel<<<cdiv(n_act, 128), 128, 0, stream>>>(cell_view(), act, n_act, rate_act.p, cp, chem_stats.p, 0u);
+        launched();
+    }
     CUDA_CHECK(cudaGetLastError());
     toc(t_chem);
     stat[SSW_STAT_SINGLE_SWEEPS]++;
@@ -1031,6 +1065,14 @@ int ssw_set_cell_positions(ssw_handle *h, const double *xyz) {
 }
 
 const char *ssw_patch_note(ssw_handle *h) { return h ? h->s.patch_note.c_str() : ""; }
+
+int ssw_set_collectives(ssw_handle *h, ssw_collective_fn fn, void *ctx) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    h->s.collective = fn;
+    h->s.collective_ctx = ctx;
+    SSW_CATCH
+}
 
 int ssw_run_sweeps(ssw_handle *h, double *time_elapsed_s) {
     SSW_TRY

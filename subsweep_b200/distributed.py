@@ -50,6 +50,35 @@ def make_allreduce(device, group=None):
     return allreduce
 
 
+def make_collectives(device, group=None):
+    """Returns ``fn(op, ptr, n_per_rank, stream)``: in-place reduce-scatter (op 1) / all-gather (op 2) of
+    ``world_size`` chunks of ``n_per_rank`` f64 at ``ptr`` (ssw_collective_fn), NCCL over NVLink."""
+    import torch
+    import torch.distributed as dist
+
+    device = torch.device(device)
+    scratch = {}
+
+    def collective(op: int, ptr: int, n_per_rank: int, stream) -> None:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        t = tensor_from_pointer(ptr, n_per_rank * world, device)
+        mine = t[rank * n_per_rank:(rank + 1) * n_per_rank]
+        ext = torch.cuda.ExternalStream(stream, device=device) if stream else torch.cuda.current_stream(device)
+        with torch.cuda.device(device), torch.cuda.stream(ext):
+            if op == 1:
+                out = scratch.get(n_per_rank)
+                if out is None:
+                    out = scratch[n_per_rank] = torch.empty(n_per_rank, dtype=torch.float64, device=device)
+                dist.reduce_scatter_tensor(out, t, op=dist.ReduceOp.SUM, group=group)
+                mine.copy_(out)
+            elif op == 2:
+                dist.all_gather_into_tensor(t, mine, group=group)   # in place: the input is the output's own chunk
+            else:
+                raise ValueError(f"unknown collective {op}")
+
+    return collective
+
+
 def init_from_env(backend: str | None = None):
     """Initialise torch.distributed from torchrun's environment; returns (rank, world, local_rank)."""
     import torch

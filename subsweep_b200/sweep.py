@@ -93,6 +93,8 @@ class SweepParameters:
 
 
 AllReduce = Callable[[int, int, Optional[int]], None]   # (pointer, n_doubles, stream) -> in-place sum
+# (op, pointer, n_doubles_per_rank, stream): in-place reduce-scatter (op 1) / all-gather (op 2) over world_size chunks
+Collectives = Callable[[int, int, int, Optional[int]], None]
 
 
 def direction_shard(n_dirs: int, world_size: int, rank: int) -> tuple[int, int]:
@@ -108,7 +110,7 @@ class Sweep:
     def __init__(self, parameters: SweepParameters, grid: FlatGrid, density, ionized_hydrogen_fraction,
                  temperature, source, scale_factor: float = 1.0, device_id: int = 0, rank: int = 0,
                  world_size: int = 1, allreduce: Optional[AllReduce] = None, flags: int = 0, lib=None,
-                 positions="grid"):
+                 positions="grid", collectives: Optional[Collectives] = None):
         if parameters.rotate_directions:
             raise NotImplementedError("rotate_directions is not supported yet (DESIGN.md, out of scope)")
         self.lib = lib if lib is not None else capi.load()
@@ -158,6 +160,7 @@ class Sweep:
         self._h = C.c_void_p()
         self._check(self.lib.ssw_create(C.byref(p), C.byref(g), *(capi.dptr(a) for a in arrs), C.byref(self._h)))
         self._cb = None
+        self._coll_cb = None
         # the Position component (optional): lets the library run the all-cells sweep patch by patch
         if isinstance(positions, str):
             positions = getattr(grid, "positions", None) if positions == "grid" else None
@@ -170,6 +173,8 @@ class Sweep:
             if allreduce is None:
                 raise ValueError("world_size > 1 needs an allreduce callable")
             self.set_allreduce(allreduce)
+            if collectives is not None:
+                self.set_collectives(collectives)
 
     # -- plumbing ----------------------------------------------------------------------------
     def _check(self, rc: int) -> None:
@@ -187,6 +192,18 @@ class Sweep:
                 return -1
         self._cb = capi.ALLREDUCE_FN(trampoline)
         self._check(self.lib.ssw_set_allreduce(self._h, self._cb, None))
+
+    def set_collectives(self, fn: Collectives) -> None:
+        """Reduce-scatter / all-gather hook (ssw_set_collectives): chemistry sliced by cells instead of replicated."""
+        def trampoline(_ctx, op, buf, n, stream):
+            try:
+                fn(int(op), int(buf), int(n), int(stream) if stream else None)
+                return 0
+            except Exception as exc:   # noqa: BLE001 - reported through the C error path
+                print(f"subsweep_b200: collective hook failed: {exc!r}", file=sys.stderr)
+                return -1
+        self._coll_cb = capi.COLLECTIVE_FN(trampoline)
+        self._check(self.lib.ssw_set_collectives(self._h, self._coll_cb, None))
 
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value:

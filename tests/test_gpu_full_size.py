@@ -50,7 +50,6 @@ def test_wavefront_levels_closed_form(cuda_lib, box):
 
 def test_compiled_and_generic_paths_agree_at_full_size(cuda_lib, box, monkeypatch):
     params, g, f = box
-    monkeypatch.setenv("SSW_PATCH", "1")   # 84 directions would default to the level-barrier stream
     results = {}
     for name, flags in (("compiled", 0), ("stream", capi.FLAG_NO_PATCH_PATH), ("generic", capi.FLAG_NO_COMPILED_PATH)):
         s = Sweep(params, g, **f, flags=flags)
@@ -67,7 +66,7 @@ def test_compiled_and_generic_paths_agree_at_full_size(cuda_lib, box, monkeypatc
         # the default is the patch-ordered dataflow: 46 dependent macro-tile levels instead of 382 wavefront levels
         assert (s.stat("patch_macro_tiles") > 0) == (name == "compiled"), s.patch_note()
         if name == "compiled":
-            assert s.stat("patch_levels") == 46
+            assert s.stat("patch_levels") == 94     # 4^3-cell patches: 3 * 31 + 1
         s.close()
     b = results["generic"]
     for a in (results["compiled"], results["stream"]):

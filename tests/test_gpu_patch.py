@@ -38,7 +38,6 @@ def run(params, g, f, flags, steps):
 ])
 def test_patch_form_matches_stream_form_on_cartesian_grids(cuda_lib, monkeypatch, n, periodic, n_dirs, patch_cells):
     monkeypatch.setenv("SSW_PATCH_CELLS", str(patch_cells))
-    monkeypatch.setenv("SSW_PATCH", "1")    # by default only direction sets of <= 24 directions take the patch form
     params, g, f = make_problem("cartesian", n, periodic, n_dirs=n_dirs, n_levels=1)
     # two steps: the first all-cells sweep is the fused build, the second one runs the compiled form
     a = run(params, g, f, 0, 2)
