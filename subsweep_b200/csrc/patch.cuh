@@ -439,7 +439,6 @@ struct PatchArgs {
     double threshold;
     uint32_t stages, stage_bytes, vmax, pc_max, smax;
     uint32_t n_cells, epoch, poll_ns;
-    uint32_t exp;             // experiments only (SSW_PATCH_EXP): bit 0 no global store, bit 1 no rate reduction
     unsigned long long *prof; // optional per-block cycles {total, dependency poll, packet wait, packets}
 };
 
@@ -509,7 +508,9 @@ patch_sweep_kernel(PatchArgs a) {
             if (tid < n_dep) {
                 if (PROFILE && tid == 0) tp = clock64();
                 const unsigned int *flag = a.mt_flag + dep[tid];
-                while (ld_acquire_gpu(flag) != a.epoch) __nanosleep(a.poll_ns);
+                // relaxed polls (no L1 invalidation per round trip), one acquire fence once the flag is there
+                while (ld_relaxed_gpu(flag) != a.epoch) __nanosleep(a.poll_ns);
+                fence_acq_rel_gpu();
                 if (PROFILE && tid == 0) t_poll += clock64() - tp;
             }
             __syncthreads();
@@ -573,7 +574,7 @@ patch_sweep_kernel(PatchArgs a) {
                 // HydrogenOnly::get_outgoing_rate, hydrogen_only/mod.rs:81-87
                 const double out = (total < threshold) ? 0.0 : total * rec.x;
                 val[lslot0 + tid] = out;
-                if (!(a.exp & 1u)) __stcg(out_slot + gslot0 + lslot0 + tid, out);
+                __stcg(out_slot + gslot0 + lslot0 + tid, out);
                 s_inc[lc * kdg + (lcj >> 10)] = in_loc;                 // incoming_total_rate[d], summed per cell when the macro-tile is done
             }
             if (PROFILE && tid == 0) { const long long t = clock64(); t_cmp += t - tq; tq = t; }
@@ -1075,7 +1076,6 @@ inline void run_patch(Compiled &C, const GridView &g, const uint32_t *pcells, co
     a.n_cells = C.n_cells;
     a.epoch = ++C.epoch;
     a.poll_ns = env_u32("SSW_STREAM_POLL_NS", 20);
-    a.exp = env_u32("SSW_PATCH_EXP", 0);
     a.prof = nullptr;
     unsigned long long *prof_dev = nullptr;
     if (env_u32("SSW_STREAM_PROFILE", 0)) {
@@ -1113,9 +1113,9 @@ inline void run_patch(Compiled &C, const GridView &g, const uint32_t *pcells, co
             head += (double)h[10 * b + 8];
             tmax = std::max(tmax, (double)h[10 * b]);
         }
-        fprintf(stderr, "[patch phases] thread 0, cycles per tile: compute %.0f  (unused %.0f)  barrier %.0f  post %.0f  mbar wait (all packets) %.0f;  "
+        fprintf(stderr, "[patch phases] thread 0, cycles per tile: compute %.0f  barrier %.0f  post %.0f  mbar wait (all packets) %.0f;  "
                         "cycles per head (incl. poll) %.0f\n",
-                cmp / C.n_tiles, scan / C.n_tiles, bar / C.n_tiles, post / C.n_tiles, pkt / packets, head / C.n_mt);
+                cmp / C.n_tiles, bar / C.n_tiles, post / C.n_tiles, pkt / packets, head / C.n_mt);
         fprintf(stderr, "[patch profile] blocks %u (%u/SM x %u thr) macro-tiles %u tiles %u  cycles/block mean %.0f max %.0f  "
                         "dependency poll %.1f%%  packet wait %.1f%%  cycles per packet %.0f  patch levels %u  vmax %u stage %u B x %u\n",
                 C.n_blocks, C.bps, C.threads, C.n_mt, C.n_tiles, tot / C.n_blocks, tmax, 100.0 * poll / tot, 100.0 * pkt / tot,
