@@ -164,7 +164,10 @@ int ssw_run_sweeps(ssw_handle *h, double *time_elapsed_s);
 int ssw_set_inputs(ssw_handle *h, const double *density, const double *source);
 
 /* -- read-back (src/sweep/mod.rs:718-738, :612-632, :234-245) ---------------------------- */
-int ssw_read(ssw_handle *h, ssw_field field, double *out /* N */);
+/* In a direction-sharded job every rank holds the same cell state; the rank that owns the output (rank 0)
+ * reads it back, the others may pass out = NULL: they then only take part in the collective a field needs
+ * (PHOTON_RATE and the chemistry outputs sum over all directions) and copy nothing to the host. */
+int ssw_read(ssw_handle *h, ssw_field field, double *out /* N, or NULL on worker ranks */);
 int ssw_read_levels(ssw_handle *h, uint8_t *out /* N */);
 int ssw_level_counts(ssw_handle *h, uint64_t *out /* n_levels, cumulative: #cells with level >= l */);
 int ssw_lowest_allowed_level(ssw_handle *h, int32_t *out);

@@ -420,14 +420,76 @@ __device__ __forceinline__ void mini_task(const SweepArgs &a, const MiniView &m,
     __stcg(a.incoming + (size_t)dl * N + c, inc);
 }
 
-// every wavefront level fits one block: block barrier between levels
-__global__ void __launch_bounds__(512)
+// every wavefront level fits one block: block barrier between levels.  The records of a task are static, so a
+// thread loads everything its task of the NEXT level needs (offsets, own state index, the first four upwind entries,
+// the cell's absorption, source and lagged periodic term) while the gathers of the current level are in flight:
+// a level then costs one dependent round trip (the state gather) instead of three.
+constexpr int kMiniSmallThreads = 768;
+struct MiniPre {
+    uint32_t valid, i, task, e0, e1, self, src[4];
+    double ttot, w[4], att, add, per;   // add = source / D, per = lagged periodic_source
+};
+__device__ __forceinline__ MiniPre mini_prefetch(const SweepArgs &a, const MiniView &m, const uint32_t *__restrict__ queue,
+                                                 uint32_t i, bool valid) {
+    MiniPre p;
+    p.valid = valid ? 1u : 0u;
+    p.i = i;
+    if (!valid) return p;
+    const uint32_t N = a.g.n_cells;
+    p.task = queue[i];
+    const uint32_t dl = p.task / N, c = p.task - dl * N;
+    p.e0 = m.off[i];
+    p.e1 = m.off[i + 1];
+    p.self = m.self[i];
+    p.ttot = m.ttot[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool ok = p.e0 + j < p.e1;
+        p.src[j] = ok ? m.src[p.e0 + j] : 0u;
+        p.w[j] = ok ? m.w[p.e0 + j] : 0.0;
+    }
+    p.att = a.att[c];
+    p.add = a.src[c] / a.n_dirs_total;                           // site.rs:49-56
+    const int32_t pp = a.pidx[c];
+    p.per = pp >= 0 ? a.per_lag[(size_t)dl * a.n_periodic + pp] : 0.0;
+    return p;
+}
+__device__ __forceinline__ void mini_solve(const SweepArgs &a, const MiniView &m, const MiniPre &p) {
+    if (!p.valid) return;
+    const uint32_t N = a.g.n_cells;
+    const double *state = a.st.slot_of ? a.st.out_slot : a.st.q;
+    double v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = p.e0 + j < p.e1 ? __ldcg(state + p.src[j]) : 0.0;
+    double in = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (p.e0 + j < p.e1) in += v[j] * p.w[j];
+    for (uint32_t e = p.e0 + 4; e < p.e1; ++e) in += __ldcg(state + m.src[e]) * m.w[e];   // same order as mini_task
+    const double inc = in + p.add;
+    const double total = inc + p.per;
+    const double out = (total < a.threshold) ? 0.0 : total * p.att;
+    if (a.st.slot_of) __stcg(a.st.out_slot + p.self, out);
+    else __stcg(a.st.q + p.self, p.ttot > 0.0 ? out / p.ttot : 0.0);
+    const uint32_t dl = p.task / N, c = p.task - dl * N;
+    __stcg(a.incoming + (size_t)dl * N + c, inc);
+}
+__global__ void __launch_bounds__(kMiniSmallThreads)
 mini_replay_small_kernel(SweepArgs a, MiniView m, const uint32_t *__restrict__ queue,
                          const uint32_t *__restrict__ level_off, uint32_t n_levels) {
+    if (n_levels == 0) return;
+    uint32_t s = level_off[0], e = level_off[1];
+    MiniPre cur = mini_prefetch(a, m, queue, s + threadIdx.x, s + threadIdx.x < e);
     for (uint32_t lvl = 0; lvl < n_levels; ++lvl) {
-        const uint32_t s = level_off[lvl], e = level_off[lvl + 1];
-        for (uint32_t i = s + threadIdx.x; i < e; i += blockDim.x) mini_task(a, m, i, queue[i]);
-        __syncthreads();
+        uint32_t s2 = e, e2 = e;
+        if (lvl + 1 < n_levels) e2 = level_off[lvl + 2];
+        const MiniPre nxt = mini_prefetch(a, m, queue, s2 + threadIdx.x, s2 + threadIdx.x < e2);
+        mini_solve(a, m, cur);
+        for (uint32_t i = s + threadIdx.x + blockDim.x; i < e; i += blockDim.x) mini_task(a, m, i, queue[i]);
+        __syncthreads();   // global writes of this level are visible to the block's next level
+        cur = nxt;
+        s = s2;
+        e = e2;
     }
 }
 

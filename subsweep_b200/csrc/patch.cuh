@@ -397,27 +397,46 @@ p_fill_kernel(PFillArgs a) {
 }
 
 // sum_d periodic_source of the NEW outgoing rates (site.rs:53-56; handle_local_periodic_neighbour,
-// src/sweep/mod.rs:505-513, in gather form): one warp per periodic cell, lanes over directions
-__global__ void __launch_bounds__(256)
-p_periodic_rate_kernel(GridView g, const uint32_t *__restrict__ pcells, uint32_t n_periodic, uint32_t n_dl,
-                       const uint32_t *__restrict__ slot_of, const double *__restrict__ ttot_slot,
-                       const double *__restrict__ out_slot, double *__restrict__ acc_per) {
-    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
-    if (wid >= n_periodic) return;
-    const uint32_t c = pcells[wid];
+// src/sweep/mod.rs:505-513, in gather form).  The periodic upwind entries of every periodic cell are static:
+// they are listed once (donor slot, share), ordered by (periodic cell, direction, face), and summed after
+// every sweep by one warp per periodic cell (strided partial sums, one xor-shuffle tree: deterministic).
+// fill == false: cnt[p] = number of entries; fill == true: writes the entries at off[p]
+__global__ void __launch_bounds__(128)
+p_periodic_list_kernel(GridView g, const uint32_t *__restrict__ pcells, uint32_t n_periodic, uint32_t n_dl,
+                       const uint32_t *__restrict__ slot_of, const double *__restrict__ ttot_slot, bool fill,
+                       uint32_t *__restrict__ cnt, const uint32_t *__restrict__ off, uint32_t *__restrict__ src_out,
+                       double *__restrict__ w_out) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_periodic) return;
+    const uint32_t c = pcells[p];
     const uint32_t f0 = g.face_off[c], f1 = g.face_off[c + 1];
-    double sum = 0.0;
-    for (uint32_t dl = lane; dl < n_dl; dl += 32) {
+    uint32_t m = fill ? off[p] : 0u;
+    for (uint32_t dl = 0; dl < n_dl; ++dl) {
         const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
         for (uint32_t f = f0; f < f1; ++f) {
             if (g.face_kind[f] != 2) continue;
             const double dd = dot_dir(ld_geo(g.face_geo + f), dx, dy, dz);
             if (!(dd < 0.0)) continue;
-            const uint32_t src = slot_of[(size_t)dl * g.n_cells + (uint32_t)g.face_nb[f]];
-            const double tt = ttot_slot[src];
-            if (tt > 0.0) sum += __ldcg(out_slot + src) * ((g.face_rev[f] * (-dd)) / tt);
+            if (fill) {
+                const uint32_t src = slot_of[(size_t)dl * g.n_cells + (uint32_t)g.face_nb[f]];
+                const double tt = ttot_slot[src];
+                src_out[m] = src;
+                w_out[m] = tt > 0.0 ? (g.face_rev[f] * (-dd)) / tt : 0.0;
+            }
+            ++m;
         }
     }
+    if (!fill) cnt[p] = m;
+}
+
+__global__ void __launch_bounds__(256)
+p_periodic_rate_kernel(const uint32_t *__restrict__ off, const uint32_t *__restrict__ src, const double *__restrict__ w,
+                       uint32_t n_periodic, const double *__restrict__ out_slot, double *__restrict__ acc_per) {
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (wid >= n_periodic) return;
+    const uint32_t e0 = off[wid], e1 = off[wid + 1];
+    double sum = 0.0;
+    for (uint32_t e = e0 + lane; e < e1; e += 32) sum += __ldcg(out_slot + src[e]) * w[e];
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (lane == 0) acc_per[wid] = sum;
 }
@@ -677,7 +696,8 @@ inline uint32_t make_direction_groups(const double *dirs_local, uint32_t n_dl, u
 // PatchUnsupported when the grid does not admit the form (the caller falls back to compile_schedule).
 inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGrid &pg, const double *dirs_local,
                                    const uint32_t *tasks, const uint32_t *level_off_dev, uint64_t n_tasks,
-                                   uint32_t n_levels, int n_local_dirs, uint32_t n_periodic, const double *q_nat,
+                                   uint32_t n_levels, int n_local_dirs, const uint32_t *pcells, uint32_t n_periodic,
+                                   const double *q_nat,
                                    int num_sms, cudaStream_t stream, uint64_t *launch_counter) {
     C.release();
     if (n_tasks >= 0x7fffff00ull) throw PatchUnsupported("more than 2^31 tasks per rank");
@@ -1021,6 +1041,32 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
         if (cnt_h[1] != n_lag) throw std::runtime_error("compile_patch_schedule: periodic snapshot count mismatch");
         if (cnt_h[3]) throw std::runtime_error("compile_patch_schedule: a task reads a slot of a later sub-level");
 
+        // static list of the periodic upwind entries per periodic cell (the periodic_source term of the rate)
+        if (n_periodic) {
+            DTmp<uint32_t> pcnt;
+            pcnt.alloc((size_t)n_periodic + 1, "pcnt");
+            cuda_ok(cudaMalloc(&C.per_off, sizeof(uint32_t) * ((size_t)n_periodic + 1)), "malloc per_off");
+            cuda_ok(cudaMemsetAsync(pcnt.p + n_periodic, 0, sizeof(uint32_t), stream), "memset");
+            const unsigned pb = (n_periodic + 127) / 128;
+            p_periodic_list_kernel<<<pb, 128, 0, stream>>>(g, pcells, n_periodic, n_dl, C.slot_of, C.ttot_slot, false, pcnt.p,
+                                                          nullptr, nullptr, nullptr);
+            size_t bytes = 0;
+            DTmp<unsigned char> temp;
+            cuda_ok(cub::DeviceScan::ExclusiveSum(nullptr, bytes, pcnt.p, C.per_off, (int)n_periodic + 1, stream), "scan size");
+            temp.alloc(bytes, "scan temp");
+            cuda_ok(cub::DeviceScan::ExclusiveSum(temp.p, bytes, pcnt.p, C.per_off, (int)n_periodic + 1, stream), "scan");
+            uint32_t n_pe = 0;
+            cuda_ok(cudaMemcpyAsync(&n_pe, C.per_off + n_periodic, sizeof n_pe, cudaMemcpyDeviceToHost, stream), "copy");
+            cuda_ok(cudaStreamSynchronize(stream), "periodic list sync");
+            if (n_pe != n_lag) throw std::runtime_error("compile_patch_schedule: periodic entry count mismatch");
+            cuda_ok(cudaMalloc(&C.per_src, sizeof(uint32_t) * (size_t)std::max<uint32_t>(n_pe, 1)), "malloc per_src");
+            cuda_ok(cudaMalloc(&C.per_w, sizeof(double) * (size_t)std::max<uint32_t>(n_pe, 1)), "malloc per_w");
+            p_periodic_list_kernel<<<pb, 128, 0, stream>>>(g, pcells, n_periodic, n_dl, C.slot_of, C.ttot_slot, true, nullptr,
+                                                          C.per_off, C.per_src, C.per_w);
+            cuda_ok(cudaStreamSynchronize(stream), "periodic list sync");
+            launches += 4;
+        }
+
         C.threads = threads;
         C.bps = (uint32_t)per_sm;
         C.stages = stages;
@@ -1056,8 +1102,7 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
 
 // One all-cells sweep over the patch-ordered schedule.  Leaves sum_d incoming per (group, cell) in C.acc_cell
 // and sum_d periodic_source per periodic cell in C.acc_per (s_rate_finish_kernel folds them).
-inline void run_patch(Compiled &C, const GridView &g, const uint32_t *pcells, const double2 *cellrec, double threshold,
-                      cudaStream_t stream, uint64_t *launch_counter) {
+inline void run_patch(Compiled &C, const double2 *cellrec, double threshold, cudaStream_t stream, uint64_t *launch_counter) {
     PatchArgs a;
     a.stream = C.stream;
     a.stream_off = C.stream_off;
@@ -1096,9 +1141,8 @@ inline void run_patch(Compiled &C, const GridView &g, const uint32_t *pcells, co
     cuda_ok(cudaLaunchCooperativeKernel((const void *)kernel, dim3(C.n_blocks), dim3(C.threads), args, smem, stream),
             "patch_sweep_kernel launch");
     if (C.n_periodic) {
-        const uint32_t n_dl = (uint32_t)(C.n_tasks / C.n_cells);
         p_periodic_rate_kernel<<<(unsigned)(((size_t)C.n_periodic * 32 + 255) / 256), 256, 0, stream>>>(
-            g, pcells, C.n_periodic, n_dl, C.slot_of, C.ttot_slot, C.out_slot, C.acc_per);
+            C.per_off, C.per_src, C.per_w, C.n_periodic, C.out_slot, C.acc_per);
         ++launches;
     }
     if (prof_dev) {

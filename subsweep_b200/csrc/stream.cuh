@@ -141,6 +141,8 @@ struct Compiled {
     uint32_t kd = 0, n_patches = 0, patch_levels = 0;
     unsigned int *mt_flag = nullptr;   // n_mt: epoch of the sweep that last completed the macro-tile
     PDesc *ptab = nullptr;             // packet table, block-major
+    uint32_t *per_off = nullptr, *per_src = nullptr;   // periodic upwind entries per periodic cell (CSR)
+    double *per_w = nullptr;
     Compiled() = default;
     Compiled(const Compiled &) = delete;
     Compiled &operator=(const Compiled &) = delete;
@@ -148,7 +150,9 @@ struct Compiled {
     void release() {
         cudaFree(slot_of); cudaFree(out_slot); cudaFree(ttot_slot); cudaFree(lag_src); cudaFree(stream);
         cudaFree(tab); cudaFree(tab_off); cudaFree(stream_off); cudaFree(lvl_target); cudaFree(lvl_dep);
-        cudaFree(lvl_count); cudaFree(acc_cell); cudaFree(acc_per); cudaFree(mt_flag); cudaFree(ptab);
+        cudaFree(lvl_count); cudaFree(acc_cell); cudaFree(acc_per); cudaFree(mt_flag); cudaFree(ptab); cudaFree(per_off); cudaFree(per_src); cudaFree(per_w);
+        per_off = per_src = nullptr;
+        per_w = nullptr;
         mt_flag = nullptr;
         ptab = nullptr;
         patch_mode = false;

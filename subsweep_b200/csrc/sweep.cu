@@ -763,7 +763,7 @@ void Sweep::single_sweep(int cur) {
                 if (have_patches && !(P.flags & SSW_FLAG_NO_PATCH_PATH) && want_patch) {
                     try {
                         compile_patch_schedule(S.compiled, grid_view(), patch_view(), dirs_all.data() + 3 * (size_t)d0,
-                                               S.tasks.p, S.level_off.p, S.n_tasks, S.n_levels, Dl, n_periodic, q.p,
+                                               S.tasks.p, S.level_off.p, S.n_tasks, S.n_levels, Dl, pcells.p, n_periodic, q.p,
                                                num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
                         patched = true;
                         patch_note.clear();
@@ -790,7 +790,7 @@ void Sweep::single_sweep(int cur) {
                 cellrec_kernel<<<cdiv(N, 256), 256, 0, stream>>>(att.p, src.p, (double)D, N, cellrec.p);
                 launched();
                 if (S.compiled.patch_mode)
-                    run_patch(S.compiled, grid_view(), pcells.p, cellrec.p, P.significant_rate_threshold_per_s, stream,
+                    run_patch(S.compiled, cellrec.p, P.significant_rate_threshold_per_s, stream,
                               &stat[SSW_STAT_KERNEL_LAUNCHES]);
                 else
                     run_compiled(S.compiled, cellrec.p, P.significant_rate_threshold_per_s, stream,
@@ -810,7 +810,7 @@ void Sweep::single_sweep(int cur) {
             if (want_mini && S.mini_valid) {
                 MiniView mv = S.mini_view();
                 if (S.max_level_tasks <= 2048) {
-                    mini_replay_small_kernel<<<1, 512, 0, stream>>>(a, mv, qp, lo, nl);
+                    mini_replay_small_kernel<<<1, kMiniSmallThreads, 0, stream>>>(a, mv, qp, lo, nl);
                 } else {
                     void *margs[] = {&a, &mv, &qp, &lo, &nl};
                     const unsigned blocks = std::max(1u, std::min<unsigned>((unsigned)coop_blocks_mini, cdiv(S.max_level_tasks, 256)));
@@ -992,7 +992,8 @@ void Sweep::read_field(int field, double *out) {
     default: fail(SSW_E_INVALID, "unknown field %d", field);
     }
     CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaMemcpyAsync(out, srcp, sizeof(double) * N, cudaMemcpyDeviceToHost, stream));
+    // out == NULL: a worker rank of a sharded job takes part in the field's collective but keeps no host copy
+    if (out) CUDA_CHECK(cudaMemcpyAsync(out, srcp, sizeof(double) * N, cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
@@ -1100,7 +1101,7 @@ int ssw_set_inputs(ssw_handle *h, const double *density, const double *source) {
 int ssw_read(ssw_handle *h, ssw_field field, double *out) {
     SSW_TRY
     REQUIRE_HANDLE(h);
-    if (!out) ssw::fail(SSW_E_INVALID, "null out pointer");
+    if (!out && h->s.P.world_size <= 1) ssw::fail(SSW_E_INVALID, "null out pointer");
     h->s.read_field((int)field, out);
     h->s.resolve_timers();
     SSW_CATCH

@@ -248,6 +248,10 @@ class Sweep:
         self._check(self.lib.ssw_read(self._h, capi.FIELDS[field_name], capi.dptr(out)))
         return out
 
+    def read_as_worker(self, field_name: str) -> None:
+        """Worker rank of a sharded job: take part in the field's collective, copy nothing (ssw_read with NULL)."""
+        self._check(self.lib.ssw_read(self._h, capi.FIELDS[field_name], None))
+
     def time_series(self, mass=None, with_rates: bool = False) -> dict:
         """compute_time_series_system (src/sweep/time_series.rs:61-155), reduced on the device; keys are the
         reference's time-series names."""
