@@ -490,9 +490,9 @@ void Sweep::set_positions(const double *xyz) {
     for (int k = 0; k < 3; ++k)
         if (hi[k] > lo[k]) { ++dims; vol *= hi[k] - lo[k]; }
     // patch size: a direction shard (few local directions) is bound by the chain of dependent macro-tiles -> large
-    // patches (8^3), few levels; with many directions the sweep is throughput-bound and small patches (4^3) keep far
+    // patches (8^3), few levels; with many directions the sweep is throughput-bound and small patches (5^3) keep
     // more macro-tiles resident per SM (measured on B200)
-    double target = (double)stream_env_u32("SSW_PATCH_CELLS", Dl <= 24 ? 512 : 64);
+    double target = (double)stream_env_u32("SSW_PATCH_CELLS", Dl <= 24 ? 512 : 125);
     target = std::min<double>(std::max<double>(target, 8.0), (double)kMaxPatchCells);
     std::vector<uint32_t> pof(N), poff, pcl(N);
     std::vector<uint16_t> lidx(N);
