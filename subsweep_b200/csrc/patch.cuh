@@ -461,66 +461,6 @@ struct PatchArgs {
     unsigned long long *prof; // optional per-block cycles {total, dependency poll, packet wait, packets}
 };
 
-// What a thread needs from a tile packet before it can touch the macro-tile's values: the tile's header fields and, for
-// its own slot, cell / direction index, entry range, the first four (value index, share) pairs and the cell record.
-// All of it is static, so it is loaded for the NEXT tile while the current one is still waiting at its barrier
-// (software pipeline): behind the barrier only the shared-memory gathers of the values and the f64 chain remain.
-struct TilePre {
-    uint32_t valid;                    // this thread holds the data of the packet it is about to process
-    uint32_t n, lslot0, last;          // header: slots, first slot inside the macro-tile, last tile of the macro-tile
-    uint32_t next_off16, next_bytes;   // header: refill of the ring stage
-    uint32_t w_off, idx_off;           // shared-memory byte addresses of the share / value-index sections
-    uint32_t lcj, e0, em, e1;          // own slot (tid < n)
-    uint32_t vi[4];
-    double wv[4];
-    double2 rec;
-};
-__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok;
-}
-__device__ __forceinline__ void load_tile(TilePre &t, const unsigned char *pkt, const PHdr &h, uint32_t tid, const double2 *s_rec) {
-    t.valid = 1u;
-    t.n = h.n; t.lslot0 = h.c32; t.last = h.b16 & 1u;
-    t.next_off16 = h.next_off16; t.next_bytes = h.next_bytes;
-    const double *const w = reinterpret_cast<const double *>(pkt + sizeof(PHdr));
-    const uint16_t *const idx = reinterpret_cast<const uint16_t *>(pkt + ((h.gslot0 & 0xffffu) << 4));
-    t.w_off = smem_u32(w);
-    t.idx_off = smem_u32(idx);
-    t.lcj = 0; t.e0 = 0; t.em = 0; t.e1 = 0;
-    t.rec = make_double2(0.0, 0.0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { t.vi[j] = 0u; t.wv[j] = 0.0; }
-    if (tid < t.n) {
-        const uint16_t *const lcell = reinterpret_cast<const uint16_t *>(pkt + ((h.gslot0 >> 16) << 4));
-        const uint32_t *const info = reinterpret_cast<const uint32_t *>(pkt + (h.n_slots << 4));
-        t.lcj = lcell[tid];                      // patch-local cell | index of the direction inside its group << 10
-        const uint32_t inf = info[tid];
-        t.e1 = info[tid + 1] & 0xffffu;
-        t.e0 = inf & 0xffffu;
-        t.em = t.e1 - ((inf >> 16) & 0xffu);
-        t.rec = s_rec[t.lcj & 0x3ffu];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool ok = t.e0 + j < t.em;
-            t.vi[j] = ok ? idx[t.e0 + j] : 0u;
-            t.wv[j] = ok ? w[t.e0 + j] : 0.0;
-        }
-    }
-}
-__device__ __forceinline__ double lds_f64(uint32_t addr) {
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-
 template <int THREADS, int MIN_BLOCKS, bool PROFILE>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 patch_sweep_kernel(PatchArgs a) {
@@ -559,21 +499,14 @@ patch_sweep_kernel(PatchArgs a) {
     }
     uint32_t gslot0 = 0, n_slots = 0, group = 0, rank = 0, n_cells = 0, kdg = 1;
     uint32_t stage = 0, parity = 0;
-    long long t_begin = 0, t_poll = 0, t_pkt = 0, tp = 0, t_cmp = 0, t_bar = 0, t_post = 0, t_head = 0, tq = 0;
-    unsigned long long n_pre = 0;
+    long long t_begin = 0, t_poll = 0, t_pkt = 0, tp = 0, t_cmp = 0, t_scan = 0, t_bar = 0, t_post = 0, t_head = 0, tq = 0;
     if (PROFILE && tid == 0) t_begin = clock64();
-    TilePre pre;
-    pre.valid = 0u;
     for (uint32_t k = 0; k < n_my; ++k) {
+        if (PROFILE && tid == 0) tp = clock64();
+        mbar_wait(smem_u32(full + stage), parity);
+        if (PROFILE && tid == 0) t_pkt += clock64() - tp;
         unsigned char *const pkt = ring + (size_t)stage * stage_bytes;
-        PHdr h;
-        h.kind = 0;
-        if (!pre.valid) {   // (after a prefetch this thread has already seen the packet land)
-            if (PROFILE && tid == 0) tp = clock64();
-            mbar_wait(smem_u32(full + stage), parity);
-            if (PROFILE && tid == 0) t_pkt += clock64() - tp;
-            h = *reinterpret_cast<const PHdr *>(pkt);
-        }
+        const PHdr h = *reinterpret_cast<const PHdr *>(pkt);
         if (PROFILE && tid == 0) tq = clock64();
         if (h.kind) {
             // ---- macro-tile head: stage the patch's cell data, wait for the upwind macro-tiles, gather the
@@ -619,57 +552,59 @@ patch_sweep_kernel(PatchArgs a) {
                 mbar_expect_tx(smem_u32(full + stage), h.next_bytes);
                 tma_bulk_load(smem_u32(pkt), stream + (size_t)h.next_off16 * 16u, h.next_bytes, smem_u32(full + stage), policy);
             }
-            if (PROFILE && tid == 0) t_head += clock64() - tq;
         } else {
             // ---- one tile: <= THREADS tasks of one sub-level; every value it reads is in shared memory
-            if (!pre.valid) load_tile(pre, pkt, h, tid, s_rec);
-            else if (PROFILE && tid == 0) ++n_pre;
-            if (tid < pre.n) {   // (warps beyond the tile's slots only keep the barrier)
-                double vv[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) vv[j] = val[pre.vi[j]];
+            const uint32_t n = h.n, lslot0 = h.c32;
+            const double *const w = reinterpret_cast<const double *>(pkt + sizeof(PHdr));
+            const uint16_t *const idx = reinterpret_cast<const uint16_t *>(pkt + ((h.gslot0 & 0xffffu) << 4));
+            const uint16_t *const lcell = reinterpret_cast<const uint16_t *>(pkt + ((h.gslot0 >> 16) << 4));
+            const uint32_t *const info = reinterpret_cast<const uint32_t *>(pkt + (h.n_slots << 4));
+            if (tid < n) {   // (warps beyond the tile's slots only keep the barrier)
+                const uint32_t lcj = lcell[tid];   // patch-local cell | index of the direction inside its group << 10
+                const uint32_t inf = info[tid];
+                const uint32_t e1 = info[tid + 1] & 0xffffu;
+                const uint32_t lc = lcj & 0x3ffu;
+                const double2 rec = s_rec[lc];
+                uint32_t e = inf & 0xffffu;
+                const uint32_t em = e1 - ((inf >> 16) & 0xffu);
                 double in_loc = 0.0, in_per = 0.0;
                 // product and sum rounded separately, Local faces in face order, then the periodic ones: the
-                // arithmetic of stream.cuh bit for bit
+                // arithmetic of stream.cuh bit for bit.  Four entries per round: their loads are independent,
+                // only the additions form a chain.
+#pragma unroll 1
+                for (; e < em; e += 4u) {
+                    uint32_t vi[4];
+                    double wv[4], vv[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (pre.e0 + j < pre.em) in_loc = __dadd_rn(in_loc, __dmul_rn(vv[j], pre.wv[j]));
+                    for (int j = 0; j < 4; ++j) {
+                        const bool ok = e + j < em;
+                        vi[j] = ok ? idx[e + j] : 0u;
+                        wv[j] = ok ? w[e + j] : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) vv[j] = val[vi[j]];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (e + j < em) in_loc = __dadd_rn(in_loc, __dmul_rn(vv[j], wv[j]));
+                }
 #pragma unroll 1
-                for (uint32_t e = pre.e0 + 4u; e < pre.em; ++e)   // more than four Local upwind faces: straight from the packet
-                    in_loc = __dadd_rn(in_loc, __dmul_rn(val[lds_u16(pre.idx_off + 2u * e)], lds_f64(pre.w_off + 8u * e)));
-#pragma unroll 1
-                for (uint32_t e = pre.em; e < pre.e1; ++e)
-                    in_per = __dadd_rn(in_per, __dmul_rn(val[lds_u16(pre.idx_off + 2u * e)], lds_f64(pre.w_off + 8u * e)));
-                const double total = (in_loc + pre.rec.y) + in_per;     // site.rs:49-56
+                for (uint32_t ep = em; ep < e1; ++ep) in_per = __dadd_rn(in_per, __dmul_rn(val[idx[ep]], w[ep]));
+                const double total = (in_loc + rec.y) + in_per;         // site.rs:49-56
                 // HydrogenOnly::get_outgoing_rate, hydrogen_only/mod.rs:81-87
-                const double out = (total < threshold) ? 0.0 : total * pre.rec.x;
-                val[pre.lslot0 + tid] = out;
-                __stcg(out_slot + gslot0 + pre.lslot0 + tid, out);
-                // incoming_total_rate[d], summed per cell when the macro-tile is done
-                s_inc[(pre.lcj & 0x3ffu) * kdg + (pre.lcj >> 10)] = in_loc;
+                const double out = (total < threshold) ? 0.0 : total * rec.x;
+                val[lslot0 + tid] = out;
+                __stcg(out_slot + gslot0 + lslot0 + tid, out);
+                s_inc[lc * kdg + (lcj >> 10)] = in_loc;                 // incoming_total_rate[d], summed per cell when the macro-tile is done
             }
             if (PROFILE && tid == 0) { const long long t = clock64(); t_cmp += t - tq; tq = t; }
-            // software pipeline: if the next tile of this macro-tile has already landed in the ring, pull this thread's
-            // part of it into registers now, in the shadow of the barrier
-            TilePre nxt;
-            nxt.valid = 0u;
-            if (!pre.last) {
-                const uint32_t ns = stage + 1u == stages ? 0u : stage + 1u;
-                const uint32_t np = stage + 1u == stages ? parity ^ 1u : parity;
-                if (mbar_test(smem_u32(full + ns), np)) {
-                    const unsigned char *const pkt2 = ring + (size_t)ns * stage_bytes;
-                    const PHdr h2 = *reinterpret_cast<const PHdr *>(pkt2);
-                    load_tile(nxt, pkt2, h2, tid, s_rec);
-                }
-            }
             __syncthreads();   // this sub-level's rates are visible; every thread is done with the stage
             if (PROFILE && tid == 0) { const long long t = clock64(); t_bar += t - tq; tq = t; }
             // the ring stage was only read (generic proxy), never written: no proxy fence before the refill
-            if (tid == THREADS - 32 && pre.next_bytes) {
-                mbar_expect_tx(smem_u32(full + stage), pre.next_bytes);
-                tma_bulk_load(smem_u32(pkt), stream + (size_t)pre.next_off16 * 16u, pre.next_bytes, smem_u32(full + stage), policy);
+            if (tid == THREADS - 32 && h.next_bytes) {
+                mbar_expect_tx(smem_u32(full + stage), h.next_bytes);
+                tma_bulk_load(smem_u32(pkt), stream + (size_t)h.next_off16 * 16u, h.next_bytes, smem_u32(full + stage), policy);
             }
-            if (pre.last) {
+            if (h.b16 & 1u) {
                 // ---- macro-tile done.  Every outgoing rate of the macro-tile was stored before the barrier above, so the
                 //      done flag goes out first (the release is cumulative over the block's stores; downwind macro-tiles
                 //      are waiting for it).  Then sum_d incoming of the group's directions per cell, in direction order
@@ -685,9 +620,8 @@ patch_sweep_kernel(PatchArgs a) {
                 // no barrier: the next head fills the other s_cellid buffer, and two barriers separate it from the
                 // next write to s_inc
             }
-            if (PROFILE && tid == 0) t_post += clock64() - tq;
-            pre = nxt;
         }
+        if (PROFILE && tid == 0) { if (h.kind) t_head += clock64() - tq; else t_post += clock64() - tq; }
         if (++stage == stages) { stage = 0; parity ^= 1u; }
     }
     if (PROFILE && tid == 0) {
@@ -696,7 +630,7 @@ patch_sweep_kernel(PatchArgs a) {
         a.prof[10 * blockIdx.x + 2] = (unsigned long long)t_pkt;
         a.prof[10 * blockIdx.x + 3] = n_my;
         a.prof[10 * blockIdx.x + 4] = (unsigned long long)t_cmp;
-        a.prof[10 * blockIdx.x + 5] = n_pre;
+        a.prof[10 * blockIdx.x + 5] = (unsigned long long)t_scan;
         a.prof[10 * blockIdx.x + 6] = (unsigned long long)t_bar;
         a.prof[10 * blockIdx.x + 7] = (unsigned long long)t_post;
         a.prof[10 * blockIdx.x + 8] = (unsigned long long)t_head;
@@ -705,9 +639,9 @@ patch_sweep_kernel(PatchArgs a) {
 
 typedef void (*PatchKernel)(PatchArgs);
 inline PatchKernel patch_kernel_for(uint32_t threads, bool profile) {
-    // minimum blocks per SM: 768 resident threads (<= 85 registers; the tile pipeline keeps a second tile's data in registers)
-    if (profile) return threads == 64 ? patch_sweep_kernel<64, 12, true> : threads == 128 ? patch_sweep_kernel<128, 6, true> : patch_sweep_kernel<256, 3, true>;
-    return threads == 64 ? patch_sweep_kernel<64, 12, false> : threads == 128 ? patch_sweep_kernel<128, 6, false> : patch_sweep_kernel<256, 3, false>;
+    // minimum blocks per SM chosen so that the register file never limits residency below 1024 threads (<= 64 registers)
+    if (profile) return threads == 64 ? patch_sweep_kernel<64, 16, true> : threads == 128 ? patch_sweep_kernel<128, 8, true> : patch_sweep_kernel<256, 4, true>;
+    return threads == 64 ? patch_sweep_kernel<64, 16, false> : threads == 128 ? patch_sweep_kernel<128, 8, false> : patch_sweep_kernel<256, 4, false>;
 }
 
 template <class T>
@@ -1223,9 +1157,9 @@ inline void run_patch(Compiled &C, const double2 *cellrec, double threshold, cud
             head += (double)h[10 * b + 8];
             tmax = std::max(tmax, (double)h[10 * b]);
         }
-        fprintf(stderr, "[patch phases] thread 0, cycles per tile: compute %.0f  prefetch + barrier %.0f  post %.0f  mbar wait (all packets) %.0f;  "
-                        "cycles per head (incl. poll) %.0f;  tiles with prefetched data %.1f%%\n",
-                cmp / C.n_tiles, bar / C.n_tiles, post / C.n_tiles, pkt / packets, head / C.n_mt, 100.0 * scan / C.n_tiles);
+        fprintf(stderr, "[patch phases] thread 0, cycles per tile: compute %.0f  barrier %.0f  post %.0f  mbar wait (all packets) %.0f;  "
+                        "cycles per head (incl. poll) %.0f\n",
+                cmp / C.n_tiles, bar / C.n_tiles, post / C.n_tiles, pkt / packets, head / C.n_mt);
         fprintf(stderr, "[patch profile] blocks %u (%u/SM x %u thr) macro-tiles %u tiles %u  cycles/block mean %.0f max %.0f  "
                         "dependency poll %.1f%%  packet wait %.1f%%  cycles per packet %.0f  patch levels %u  vmax %u stage %u B x %u\n",
                 C.n_blocks, C.bps, C.threads, C.n_mt, C.n_tiles, tot / C.n_blocks, tmax, 100.0 * poll / tot, 100.0 * pkt / tot,
