@@ -84,12 +84,12 @@ constexpr uint32_t kPHead = 1u, kPLast = 2u;
 struct __align__(16) PHdr {
     uint16_t kind;     // 0 tile, 1 head
     uint16_t n;        // tile: slots; head: upwind macro-tiles to wait for
-    uint16_t a16;      // tile: overflow entries; head: cells of the patch
+    uint16_t a16;      // tile: entries; head: cells of the patch
     uint16_t b16;      // tile: bit 0 = last tile of the macro-tile; head: direction group | directions in the group << 10
     uint32_t c32;      // tile: first slot of the tile inside the macro-tile; head: external entries
     uint32_t next_off16, next_bytes;   // packet that goes into this ring stage next (bytes = 0: none)
-    uint32_t gslot0;   // head: first global slot of the macro-tile; tile: byte offset of the overflow value indices
-    uint32_t n_slots;  // head: slots of the macro-tile; tile: slots of the NEXT packet if it is a tile of the same macro-tile, else 0
+    uint32_t gslot0;   // head: first global slot of the macro-tile; tile: idx offset | lcell offset << 16 (16-B units)
+    uint32_t n_slots;  // head: slots of the macro-tile; tile: info offset (16-B units)
     uint32_t rank;     // head: index of the macro-tile's done flag
 };
 static_assert(sizeof(PHdr) == 32, "packet header is 32 bytes");
@@ -105,28 +105,16 @@ __host__ __device__ inline HeadLayout head_layout(uint32_t n_dep, uint32_t n_ext
     L.bytes = o;
     return L;
 }
-// One fixed-size record per slot: everything a task needs except the values themselves sits at an address that
-// depends only on the packet base and the thread index, so a thread can load the record of its NEXT tile with three
-// independent 16-byte loads while the current tile computes (no header -> offsets -> entries chain).
-struct __align__(16) SlotRec {
-    uint16_t lcj;      // patch-local cell | index of the direction inside its group << 10
-    uint8_t n_fix;     // Local upwind entries in the record (<= 4)
-    uint8_t n_ovf;     // further Local entries in the overflow section
-    uint16_t vi[4];    // value indices: < n_slots -> outgoing rate of a slot of this macro-tile, else n_slots + external entry
-    uint16_t ovf;      // first overflow entry of the slot: [further Local entries][periodic entries]
-    uint8_t n_per;     // periodic entries (always in the overflow section)
-    uint8_t pad;
-    double w[4];       // shares A_rev (-n.d) / sum_downwind(A n.d) of the donors
-};
-static_assert(sizeof(SlotRec) == 48, "slot record is 48 bytes");
-struct PTileLayout { uint32_t rec, w, idx, bytes; };
-// tile packet = [header][SlotRec[n]][f64 overflow share[Eo]][u16 overflow value index[Eo]]
-__host__ __device__ inline PTileLayout ptile_layout(uint32_t n, uint32_t Eo) {
+struct PTileLayout { uint32_t w, idx, lcell, info, bytes; };
+// tile packet = [header][f64 share[E]][u16 value index[E]][u16 patch-local cell[n]][u32 info[n + 1]]
+// value index: < n_slots -> outgoing rate of a slot of this macro-tile, else n_slots + external entry
+__host__ __device__ inline PTileLayout ptile_layout(uint32_t n, uint32_t E) {
     PTileLayout L;
     uint32_t o = (uint32_t)sizeof(PHdr);
-    L.rec = o; o += 48u * n;
-    L.w = o;   o += align16(8u * Eo);
-    L.idx = o; o += align16(2u * Eo);
+    L.w = o;     o += align16(8u * E);
+    L.idx = o;   o += align16(2u * E);
+    L.lcell = o; o += align16(2u * n);
+    L.info = o;  o += align16(4u * (n + 1u));
     L.bytes = o;
     return L;
 }
@@ -232,7 +220,7 @@ p_pl_rank_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__
 __global__ void __launch_bounds__(256)
 p_count_kernel(GridView g, const uint32_t *__restrict__ k32, uint32_t n, uint32_t n_dl,
                const uint32_t *__restrict__ patch_of, uint32_t *__restrict__ cnt_e, uint32_t *__restrict__ cnt_x,
-               uint32_t *__restrict__ cnt_o, double *__restrict__ ttot_slot, unsigned int *counters) {
+               double *__restrict__ ttot_slot, unsigned int *counters) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const uint32_t k = k32[s];
@@ -258,7 +246,6 @@ p_count_kernel(GridView g, const uint32_t *__restrict__ k32, uint32_t n, uint32_
     }
     cnt_e[s] = m;
     cnt_x[s] = x;
-    cnt_o[s] = (m - np > 4u ? m - np - 4u : 0u) + np;   // entries that do not fit the slot record: Local beyond four, periodic
     ttot_slot[s] = ttot;
     if (np) atomicAdd(counters, np);
     if (np > 255u) atomicExch(counters + 2, 1u);
@@ -336,32 +323,33 @@ p_fill_kernel(PFillArgs a) {
     const uint32_t t = d.id;
     const uint32_t slot0 = a.tile_start[t], n = a.tile_start[t + 1] - slot0;
     const unsigned long long e_base = a.upoff[slot0];
-    const uint32_t Eo = (uint32_t)(a.upoff[slot0 + n] - e_base);   // overflow entries of the tile
+    const uint32_t E = (uint32_t)(a.upoff[slot0 + n] - e_base);
     const uint32_t r = a.tile_rank[t];
     const uint32_t mt0 = a.mt_slot0[r], ns_mt = a.mt_slot0[r + 1] - mt0;
-    const PTileLayout L = ptile_layout(n, Eo);
-    SlotRec *recs = reinterpret_cast<SlotRec *>(pkt + L.rec);
-    double *ow = reinterpret_cast<double *>(pkt + L.w);
-    uint16_t *oidx = reinterpret_cast<uint16_t *>(pkt + L.idx);
+    const PTileLayout L = ptile_layout(n, E);
+    double *w = reinterpret_cast<double *>(pkt + L.w);
+    uint16_t *idx = reinterpret_cast<uint16_t *>(pkt + L.idx);
+    uint16_t *lcell = reinterpret_cast<uint16_t *>(pkt + L.lcell);
+    uint32_t *info = reinterpret_cast<uint32_t *>(pkt + L.info);
     uint32_t *hext = reinterpret_cast<uint32_t *>(a.stream + a.head_off[r] + sizeof(PHdr) + align16(4u * a.mt_ndep[r]));
     // zero the padding so the stream is fully initialised
     if (tid < 8) {
-        if (tid == 0 && (Eo & 1u)) ow[Eo] = 0.0;
-        const uint32_t pad_idx = (align16(2u * Eo) - 2u * Eo) / 2u;
-        if (tid < pad_idx) oidx[Eo + tid] = 0;
+        if (tid == 0 && (E & 1u)) w[E] = 0.0;
+        const uint32_t pad_idx = (align16(2u * E) - 2u * E) / 2u;
+        if (tid < pad_idx) idx[E + tid] = 0;
+        const uint32_t pad_lc = (align16(2u * n) - 2u * n) / 2u;
+        if (tid < pad_lc) lcell[n + tid] = 0xffffu;
+        const uint32_t used = n + 1u, pad_info = (align16(4u * used) - 4u * used) / 4u;
+        if (tid < pad_info) info[used + tid] = 0u;
     }
     if (tid < n) {
         const uint32_t s = slot0 + tid;
         const uint32_t k = a.k32[s];
         const uint32_t c = k / a.n_dl, dl = k - c * a.n_dl;
         const uint32_t pc = a.pg.patch_of[c];
-        SlotRec rec;
-        rec.lcj = (uint16_t)(a.pg.lidx[c] | ((uint32_t)a.group_rank[dl] << 10));
-        rec.pad = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { rec.vi[j] = 0; rec.w[j] = 0.0; }
-        const uint32_t o0 = (uint32_t)(a.upoff[s] - e_base);
-        uint32_t o = o0, n_loc = 0, n_per = 0;
+        lcell[tid] = (uint16_t)(a.pg.lidx[c] | ((uint32_t)a.group_rank[dl] << 10));
+        const uint32_t e0 = (uint32_t)(a.upoff[s] - e_base);
+        uint32_t e = e0, n_per = 0;
         uint32_t x = (uint32_t)(a.xoff[s] - a.xoff[mt0]);
         const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
         for (int pass = 0; pass < 2; ++pass) {   // Local faces first, then the periodic ones
@@ -380,6 +368,7 @@ p_fill_kernel(PFillArgs a) {
                 } else {
                     uint32_t gsrc = src;
                     if (pass) {   // periodic: the donor's pre-sweep snapshot (the reference's lag)
+                        ++n_per;
                         const unsigned int j = atomicAdd(a.counters + 1, 1u);
                         a.lag_src[j] = src;
                         gsrc = a.n_tasks + j;
@@ -388,40 +377,21 @@ p_fill_kernel(PFillArgs a) {
                     vi = ns_mt + x;
                     ++x;
                 }
-                if (pass == 0 && n_loc < 4u) {          // the record holds the first four Local entries
-                    switch (n_loc) {
-                    case 0: rec.vi[0] = (uint16_t)vi; rec.w[0] = share; break;
-                    case 1: rec.vi[1] = (uint16_t)vi; rec.w[1] = share; break;
-                    case 2: rec.vi[2] = (uint16_t)vi; rec.w[2] = share; break;
-                    default: rec.vi[3] = (uint16_t)vi; rec.w[3] = share; break;
-                    }
-                } else {                                // everything else goes to the overflow section
-                    oidx[o] = (uint16_t)vi;
-                    ow[o] = share;
-                    ++o;
-                }
-                if (pass) ++n_per; else ++n_loc;
+                idx[e] = (uint16_t)vi;
+                w[e] = share;
+                ++e;
             }
         }
-        rec.n_fix = (uint8_t)min(n_loc, 4u);
-        rec.n_ovf = (uint8_t)min(n_loc > 4u ? n_loc - 4u : 0u, 255u);
-        rec.n_per = (uint8_t)min(n_per, 255u);
-        rec.ovf = (uint16_t)o0;
-        if (n_loc > 259u) atomicExch(a.counters + 2, 1u);   // reported as an error by the host
-        recs[tid] = rec;
+        info[tid] = e0 | (min(n_per, 255u) << 16);
     }
+    __syncthreads();
     if (tid == 0) {
-        // slots of the next packet if it continues this macro-tile (the consumer prefetches its records)
-        uint32_t next_n = 0;
-        if (!(d.flags & kPLast) && blockIdx.x + 1 < a.tab_off[blk + 1]) {
-            const PDesc nd = a.ptab[blockIdx.x + 1];
-            if (!(nd.flags & kPHead)) next_n = a.tile_start[nd.id + 1] - a.tile_start[nd.id];
-        }
-        h.kind = 0; h.n = (uint16_t)n; h.a16 = (uint16_t)Eo;
+        info[n] = E;
+        h.kind = 0; h.n = (uint16_t)n; h.a16 = (uint16_t)E;
         h.b16 = (uint16_t)((d.flags & kPLast) ? 1u : 0u);
         h.c32 = slot0 - mt0;
-        h.gslot0 = L.idx;
-        h.n_slots = next_n;
+        h.gslot0 = (L.idx >> 4) | ((L.lcell >> 4) << 16);   // tile packets: section offsets in 16-B units
+        h.n_slots = L.info >> 4;
         *reinterpret_cast<PHdr *>(pkt) = h;
     }
 }
@@ -529,21 +499,13 @@ patch_sweep_kernel(PatchArgs a) {
     }
     uint32_t gslot0 = 0, n_slots = 0, group = 0, rank = 0, n_cells = 0, kdg = 1;
     uint32_t stage = 0, parity = 0;
-    long long t_begin = 0, t_poll = 0, t_pkt = 0, tp = 0, t_cmp = 0, t_bar = 0, t_post = 0, t_head = 0, tq = 0;
+    long long t_begin = 0, t_poll = 0, t_pkt = 0, tp = 0, t_cmp = 0, t_scan = 0, t_bar = 0, t_post = 0, t_head = 0, tq = 0;
     if (PROFILE && tid == 0) t_begin = clock64();
-    // software pipeline over the tiles of a macro-tile: while tile k computes, the record of this thread's slot in
-    // tile k + 1 is already on its way into registers (pq*), and the packet of tile k + 1 has been waited for
-    uint4 pq0 = make_uint4(0u, 0u, 0u, 0u);
-    double2 pq1 = make_double2(0.0, 0.0), pq2 = make_double2(0.0, 0.0);
-    uint32_t pre_valid = 0, waited = 0;
     for (uint32_t k = 0; k < n_my; ++k) {
+        if (PROFILE && tid == 0) tp = clock64();
+        mbar_wait(smem_u32(full + stage), parity);
+        if (PROFILE && tid == 0) t_pkt += clock64() - tp;
         unsigned char *const pkt = ring + (size_t)stage * stage_bytes;
-        if (!waited) {
-            if (PROFILE && tid == 0) tp = clock64();
-            mbar_wait(smem_u32(full + stage), parity);
-            if (PROFILE && tid == 0) t_pkt += clock64() - tp;
-        }
-        waited = 0;
         const PHdr h = *reinterpret_cast<const PHdr *>(pkt);
         if (PROFILE && tid == 0) tq = clock64();
         if (h.kind) {
@@ -592,57 +554,47 @@ patch_sweep_kernel(PatchArgs a) {
             }
         } else {
             // ---- one tile: <= THREADS tasks of one sub-level; every value it reads is in shared memory
-            const uint32_t n = h.n, lslot0 = h.c32, next_n = h.n_slots;
-            // the next tile of this macro-tile: make sure its packet has landed (it was requested two tiles ago), then
-            // issue the three loads of this thread's record there; they complete while this tile computes
-            uint4 nq0 = make_uint4(0u, 0u, 0u, 0u);
-            double2 nq1 = make_double2(0.0, 0.0), nq2 = make_double2(0.0, 0.0);
-            if (next_n) {
-                const uint32_t ns = stage + 1u == stages ? 0u : stage + 1u;
-                const uint32_t np = stage + 1u == stages ? parity ^ 1u : parity;
-                mbar_wait(smem_u32(full + ns), np);
-                waited = 1u;
-                if (tid < next_n) {
-                    const unsigned char *const r2 = ring + (size_t)ns * stage_bytes + sizeof(PHdr) + 48u * tid;
-                    nq0 = *reinterpret_cast<const uint4 *>(r2);
-                    nq1 = *reinterpret_cast<const double2 *>(r2 + 16);
-                    nq2 = *reinterpret_cast<const double2 *>(r2 + 32);
-                }
-            }
+            const uint32_t n = h.n, lslot0 = h.c32;
+            const double *const w = reinterpret_cast<const double *>(pkt + sizeof(PHdr));
+            const uint16_t *const idx = reinterpret_cast<const uint16_t *>(pkt + ((h.gslot0 & 0xffffu) << 4));
+            const uint16_t *const lcell = reinterpret_cast<const uint16_t *>(pkt + ((h.gslot0 >> 16) << 4));
+            const uint32_t *const info = reinterpret_cast<const uint32_t *>(pkt + (h.n_slots << 4));
             if (tid < n) {   // (warps beyond the tile's slots only keep the barrier)
-                if (!pre_valid) {   // first tile of a macro-tile: nothing was prefetched
-                    const unsigned char *const r1 = pkt + sizeof(PHdr) + 48u * tid;
-                    pq0 = *reinterpret_cast<const uint4 *>(r1);
-                    pq1 = *reinterpret_cast<const double2 *>(r1 + 16);
-                    pq2 = *reinterpret_cast<const double2 *>(r1 + 32);
-                }
-                const uint32_t lc = pq0.x & 0x3ffu, jd = (pq0.x >> 10) & 0x3fu;
-                const uint32_t n_fix = (pq0.x >> 16) & 0xffu, n_ovf = pq0.x >> 24;
-                const double v0 = val[pq0.y & 0xffffu], v1 = val[pq0.y >> 16], v2 = val[pq0.z & 0xffffu], v3 = val[pq0.z >> 16];
+                const uint32_t lcj = lcell[tid];   // patch-local cell | index of the direction inside its group << 10
+                const uint32_t inf = info[tid];
+                const uint32_t e1 = info[tid + 1] & 0xffffu;
+                const uint32_t lc = lcj & 0x3ffu;
                 const double2 rec = s_rec[lc];
-                // product and sum rounded separately, Local faces in face order, then the periodic ones: the
-                // arithmetic of stream.cuh bit for bit
+                uint32_t e = inf & 0xffffu;
+                const uint32_t em = e1 - ((inf >> 16) & 0xffu);
                 double in_loc = 0.0, in_per = 0.0;
-                if (n_fix > 0u) in_loc = __dadd_rn(in_loc, __dmul_rn(v0, pq1.x));
-                if (n_fix > 1u) in_loc = __dadd_rn(in_loc, __dmul_rn(v1, pq1.y));
-                if (n_fix > 2u) in_loc = __dadd_rn(in_loc, __dmul_rn(v2, pq2.x));
-                if (n_fix > 3u) in_loc = __dadd_rn(in_loc, __dmul_rn(v3, pq2.y));
-                const uint32_t n_per = (pq0.w >> 16) & 0xffu;
-                if (n_ovf | n_per) {   // more than four Local upwind faces, periodic faces: the packet's overflow section
-                    const double *const ow = reinterpret_cast<const double *>(pkt + sizeof(PHdr) + 48u * n);
-                    const uint16_t *const oidx = reinterpret_cast<const uint16_t *>(pkt + h.gslot0);
-                    uint32_t e = pq0.w & 0xffffu;
+                // product and sum rounded separately, Local faces in face order, then the periodic ones: the
+                // arithmetic of stream.cuh bit for bit.  Four entries per round: their loads are independent,
+                // only the additions form a chain.
 #pragma unroll 1
-                    for (const uint32_t e1 = e + n_ovf; e < e1; ++e) in_loc = __dadd_rn(in_loc, __dmul_rn(val[oidx[e]], ow[e]));
-#pragma unroll 1
-                    for (const uint32_t e2 = e + n_per; e < e2; ++e) in_per = __dadd_rn(in_per, __dmul_rn(val[oidx[e]], ow[e]));
+                for (; e < em; e += 4u) {
+                    uint32_t vi[4];
+                    double wv[4], vv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool ok = e + j < em;
+                        vi[j] = ok ? idx[e + j] : 0u;
+                        wv[j] = ok ? w[e + j] : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) vv[j] = val[vi[j]];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (e + j < em) in_loc = __dadd_rn(in_loc, __dmul_rn(vv[j], wv[j]));
                 }
+#pragma unroll 1
+                for (uint32_t ep = em; ep < e1; ++ep) in_per = __dadd_rn(in_per, __dmul_rn(val[idx[ep]], w[ep]));
                 const double total = (in_loc + rec.y) + in_per;         // site.rs:49-56
                 // HydrogenOnly::get_outgoing_rate, hydrogen_only/mod.rs:81-87
                 const double out = (total < threshold) ? 0.0 : total * rec.x;
                 val[lslot0 + tid] = out;
                 __stcg(out_slot + gslot0 + lslot0 + tid, out);
-                s_inc[lc * kdg + jd] = in_loc;                          // incoming_total_rate[d], summed per cell when the macro-tile is done
+                s_inc[lc * kdg + (lcj >> 10)] = in_loc;                 // incoming_total_rate[d], summed per cell when the macro-tile is done
             }
             if (PROFILE && tid == 0) { const long long t = clock64(); t_cmp += t - tq; tq = t; }
             __syncthreads();   // this sub-level's rates are visible; every thread is done with the stage
@@ -668,8 +620,6 @@ patch_sweep_kernel(PatchArgs a) {
                 // no barrier: the next head fills the other s_cellid buffer, and two barriers separate it from the
                 // next write to s_inc
             }
-            pq0 = nq0; pq1 = nq1; pq2 = nq2;
-            pre_valid = next_n ? 1u : 0u;
         }
         if (PROFILE && tid == 0) { if (h.kind) t_head += clock64() - tq; else t_post += clock64() - tq; }
         if (++stage == stages) { stage = 0; parity ^= 1u; }
@@ -680,7 +630,7 @@ patch_sweep_kernel(PatchArgs a) {
         a.prof[10 * blockIdx.x + 2] = (unsigned long long)t_pkt;
         a.prof[10 * blockIdx.x + 3] = n_my;
         a.prof[10 * blockIdx.x + 4] = (unsigned long long)t_cmp;
-        a.prof[10 * blockIdx.x + 5] = 0ull;
+        a.prof[10 * blockIdx.x + 5] = (unsigned long long)t_scan;
         a.prof[10 * blockIdx.x + 6] = (unsigned long long)t_bar;
         a.prof[10 * blockIdx.x + 7] = (unsigned long long)t_post;
         a.prof[10 * blockIdx.x + 8] = (unsigned long long)t_head;
@@ -689,9 +639,9 @@ patch_sweep_kernel(PatchArgs a) {
 
 typedef void (*PatchKernel)(PatchArgs);
 inline PatchKernel patch_kernel_for(uint32_t threads, bool profile) {
-    // minimum blocks per SM: <= 72 registers (the tile pipeline keeps the next tile's slot record in registers)
-    if (profile) return threads == 64 ? patch_sweep_kernel<64, 14, true> : threads == 128 ? patch_sweep_kernel<128, 7, true> : patch_sweep_kernel<256, 3, true>;
-    return threads == 64 ? patch_sweep_kernel<64, 14, false> : threads == 128 ? patch_sweep_kernel<128, 7, false> : patch_sweep_kernel<256, 3, false>;
+    // minimum blocks per SM chosen so that the register file never limits residency below 1024 threads (<= 64 registers)
+    if (profile) return threads == 64 ? patch_sweep_kernel<64, 16, true> : threads == 128 ? patch_sweep_kernel<128, 8, true> : patch_sweep_kernel<256, 4, true>;
+    return threads == 64 ? patch_sweep_kernel<64, 16, false> : threads == 128 ? patch_sweep_kernel<128, 8, false> : patch_sweep_kernel<256, 4, false>;
 }
 
 template <class T>
@@ -905,41 +855,31 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
         // 4. slots, entry counts, downwind areas
         cuda_ok(cudaMalloc(&C.slot_of, sizeof(uint32_t) * (size_t)n), "malloc slot_of");
         cuda_ok(cudaMalloc(&C.ttot_slot, sizeof(double) * (size_t)n), "malloc ttot_slot");
-        DTmp<uint32_t> cnt_e, cnt_x, cnt_o;
+        DTmp<uint32_t> cnt_e, cnt_x;
         cnt_e.alloc((size_t)n + 1, "cnt_e");
         cnt_x.alloc((size_t)n + 1, "cnt_x");
-        cnt_o.alloc((size_t)n + 1, "cnt_o");
-        DTmp<unsigned long long> tot_dev;
-        tot_dev.alloc(1, "tot");
         DTmp<unsigned long long> upoff, xoff;
         upoff.alloc((size_t)n + 1, "upoff");
         xoff.alloc((size_t)n + 1, "xoff");
         cuda_ok(cudaMemsetAsync(cnt_e.p + n, 0, sizeof(uint32_t), stream), "memset");
         cuda_ok(cudaMemsetAsync(cnt_x.p + n, 0, sizeof(uint32_t), stream), "memset");
-        cuda_ok(cudaMemsetAsync(cnt_o.p + n, 0, sizeof(uint32_t), stream), "memset");
         s_slot_scatter_kernel<<<blocks_n, 256, 0, stream>>>(k32.p, n, N, n_dl, C.slot_of);
-        p_count_kernel<<<blocks_n, 256, 0, stream>>>(g, k32.p, n, n_dl, pg.patch_of, cnt_e.p, cnt_x.p, cnt_o.p, C.ttot_slot, counters.p);
+        p_count_kernel<<<blocks_n, 256, 0, stream>>>(g, k32.p, n, n_dl, pg.patch_of, cnt_e.p, cnt_x.p, C.ttot_slot, counters.p);
         {
-            // upoff: offsets of the overflow entries (those that do not fit the slot records); xoff: external entries
-            cub::TransformInputIterator<unsigned long long, CastU64, const uint32_t *> in_e(cnt_e.p, CastU64()), in_x(cnt_x.p, CastU64()),
-                in_o(cnt_o.p, CastU64());
-            size_t bytes = 0, bytes_r = 0;
+            cub::TransformInputIterator<unsigned long long, CastU64, const uint32_t *> in_e(cnt_e.p, CastU64()), in_x(cnt_x.p, CastU64());
+            size_t bytes = 0;
             DTmp<unsigned char> temp;
-            cuda_ok(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in_o, upoff.p, (int64_t)n + 1, stream), "scan size");
-            cuda_ok(cub::DeviceReduce::Sum(nullptr, bytes_r, in_e, tot_dev.p, (int64_t)n, stream), "reduce size");
-            temp.alloc(std::max(bytes, bytes_r), "scan temp");
-            bytes = bytes_r = std::max(bytes, bytes_r);
-            cuda_ok(cub::DeviceScan::ExclusiveSum(temp.p, bytes, in_o, upoff.p, (int64_t)n + 1, stream), "scan");
+            cuda_ok(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in_e, upoff.p, (int64_t)n + 1, stream), "scan size");
+            temp.alloc(bytes, "scan temp");
+            cuda_ok(cub::DeviceScan::ExclusiveSum(temp.p, bytes, in_e, upoff.p, (int64_t)n + 1, stream), "scan");
             cuda_ok(cub::DeviceScan::ExclusiveSum(temp.p, bytes, in_x, xoff.p, (int64_t)n + 1, stream), "scan");
-            cuda_ok(cub::DeviceReduce::Sum(temp.p, bytes_r, in_e, tot_dev.p, (int64_t)n, stream), "reduce");
             cuda_ok(cudaStreamSynchronize(stream), "scan sync");
-            launches += 8;
+            launches += 6;
         }
         cnt_e.reset();
         cnt_x.reset();
-        cnt_o.reset();
         unsigned long long total_entries = 0;
-        cuda_ok(cudaMemcpy(&total_entries, tot_dev.p, sizeof total_entries, cudaMemcpyDeviceToHost), "copy");
+        cuda_ok(cudaMemcpy(&total_entries, upoff.p + n, sizeof total_entries, cudaMemcpyDeviceToHost), "copy");
         cuda_ok(cudaMemcpy(cnt_h, counters.p, sizeof cnt_h, cudaMemcpyDeviceToHost), "copy counters");
         if (cnt_h[2]) throw PatchUnsupported("a task has more than 255 periodic upwind faces");
         const uint32_t n_lag = cnt_h[0];
