@@ -519,18 +519,22 @@ patch_sweep_kernel(PatchArgs a) {
             const uint32_t *const cells = reinterpret_cast<const uint32_t *>(pkt + L.cells);
             cellid_buf ^= 1u;
             s_cellid = reinterpret_cast<uint32_t *>(smem + SL.cellid) + cellid_buf * cellid_stride;
-            for (uint32_t i = tid; i < n_cells; i += THREADS) {
-                const uint32_t c = cells[i];
-                s_cellid[i] = c;
-                s_rec[i] = __ldg(a.cellrec + c);
-            }
-            if (tid < n_dep) {
-                if (PROFILE && tid == 0) tp = clock64();
-                const unsigned int *flag = a.mt_flag + dep[tid];
-                // relaxed polls (no L1 invalidation per round trip), one acquire fence once the flag is there
-                while (ld_relaxed_gpu(flag) != a.epoch) __nanosleep(a.poll_ns);
-                fence_acq_rel_gpu();
-                if (PROFILE && tid == 0) t_poll += clock64() - tp;
+            if (tid < 32u) {
+                // warp 0 only polls: the flag round trips start at once and run beside the staging of the other warps
+                if (tid < n_dep) {
+                    if (PROFILE && tid == 0) tp = clock64();
+                    const unsigned int *flag = a.mt_flag + dep[tid];
+                    // relaxed polls (no L1 invalidation per round trip), one acquire fence once the flag is there
+                    while (ld_relaxed_gpu(flag) != a.epoch) __nanosleep(a.poll_ns);
+                    fence_acq_rel_gpu();
+                    if (PROFILE && tid == 0) t_poll += clock64() - tp;
+                }
+            } else {
+                for (uint32_t i = tid - 32u; i < n_cells; i += THREADS - 32u) {
+                    const uint32_t c = cells[i];
+                    s_cellid[i] = c;
+                    s_rec[i] = __ldg(a.cellrec + c);
+                }
             }
             __syncthreads();
             double *const vx = val + n_slots;
@@ -582,7 +586,7 @@ patch_sweep_kernel(PatchArgs a) {
                         wv[j] = ok ? w[e + j] : 0.0;
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) vv[j] = val[vi[j]];
+                    for (int j = 0; j < 4; ++j) vv[j] = e + j < em ? val[vi[j]] : 0.0;   // (no dummy reads: racecheck-clean)
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         if (e + j < em) in_loc = __dadd_rn(in_loc, __dmul_rn(vv[j], wv[j]));
