@@ -372,14 +372,25 @@ def run_b200(args) -> None:
     sync_all()
     e_tasks0 = sweep.stat("tasks_solved")
     t0 = time.perf_counter()
+    phase = {"set_inputs": 0.0, "run_sweeps": 0.0, "write_back": 0.0}
     for _ in range(args.steps):
+        ta = time.perf_counter()
         sweep.set_inputs(source=src_host)        # the Source component of this step (H2D), on every rank
+        tb = time.perf_counter()
         sweep.run_sweeps()
-        for k, buf in outs.items():              # run_sweep_system write-back (D2H), mod.rs:718-738
+        tc = time.perf_counter()
+        # run_sweep_system write-back (D2H), mod.rs:718-738: five copies queued, one synchronisation.  All ranks hold the
+        # same cell state; the rank that owns the output (0) reads it, the others only join the photon_rate all-reduce
+        for k, buf in outs.items():
             if rank == 0:
-                sweep.read(k, buf)
-            else:                                # worker ranks hold the same state; the rank that writes the output reads it
-                sweep.read_as_worker(k)
+                sweep.read_begin(k, buf)
+            elif k == "photon_rate":
+                sweep.read_begin(k, None)
+        sweep.sync()
+        td = time.perf_counter()
+        phase["set_inputs"] += tb - ta
+        phase["run_sweeps"] += tc - tb
+        phase["write_back"] += td - tc
     sync_all()
     e_wall = time.perf_counter() - t0
     e = torch.tensor([e_wall], dtype=torch.float64, device=device)
@@ -433,6 +444,7 @@ def run_b200(args) -> None:
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N * world,
                 "d2h_bytes_per_step": 8 * N * len(outs),
+                "rank0_wall_ms_per_step": {k: 1e3 * v / args.steps for k, v in phase.items()},
                 "note": "every rank uploads the step's Source component; rank 0 reads back the five result components "
                         "(all ranks hold identical cell state; worker ranks only join the photon_rate all-reduce)"},
         "gpu_launches": int(total_launches),

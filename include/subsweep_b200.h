@@ -168,6 +168,12 @@ int ssw_set_inputs(ssw_handle *h, const double *density, const double *source);
  * reads it back, the others may pass out = NULL: they then only take part in the collective a field needs
  * (PHOTON_RATE and the chemistry outputs sum over all directions) and copy nothing to the host. */
 int ssw_read(ssw_handle *h, ssw_field field, double *out /* N, or NULL on worker ranks */);
+/* The same without waiting: the copy into `out` (pinned host memory, or it degenerates to a blocking copy) is
+ * queued on the library's stream; `out` is valid after the next ssw_sync / ssw_read / ssw_run_sweeps returns.
+ * The write-back of run_sweep_system (five components, src/sweep/mod.rs:718-738) is five ssw_read_begin + one
+ * ssw_sync. */
+int ssw_read_begin(ssw_handle *h, ssw_field field, double *out);
+int ssw_sync(ssw_handle *h);
 int ssw_read_levels(ssw_handle *h, uint8_t *out /* N */);
 int ssw_level_counts(ssw_handle *h, uint64_t *out /* n_levels, cumulative: #cells with level >= l */);
 int ssw_lowest_allowed_level(ssw_handle *h, int32_t *out);

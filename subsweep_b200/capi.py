@@ -91,6 +91,8 @@ SYMBOLS = {
     "ssw_run_sweeps": (C.c_int, [H, c_double_p]),
     "ssw_set_inputs": (C.c_int, [H, c_double_p, c_double_p]),
     "ssw_read": (C.c_int, [H, C.c_int, c_double_p]),
+    "ssw_read_begin": (C.c_int, [H, C.c_int, c_double_p]),
+    "ssw_sync": (C.c_int, [H]),
     "ssw_time_series_compute": (C.c_int, [H, c_double_p, C.c_int32, C.POINTER(TimeSeries)]),
     "ssw_read_levels": (C.c_int, [H, C.POINTER(C.c_uint8)]),
     "ssw_level_counts": (C.c_int, [H, C.POINTER(C.c_uint64)]),

@@ -307,7 +307,7 @@ struct Sweep {
     void single_sweep(int cur);
     void update_timestep_levels();
     double run_sweeps();
-    void read_field(int field, double *out);
+    void read_field(int field, double *out, bool wait = true);
     void all_rates(double *dev_out);
     void maybe_allreduce(double *buf, uint64_t n);
     uint32_t cells_per_rank() const { return (uint32_t)(((uint64_t)N + P.world_size - 1) / P.world_size); }
@@ -950,7 +950,7 @@ void Sweep::all_rates(double *dev_out) {
     maybe_allreduce(dev_out, N);
 }
 
-void Sweep::read_field(int field, double *out) {
+void Sweep::read_field(int field, double *out, bool wait) {
     bind();
     const double *srcp = nullptr;
     switch (field) {
@@ -994,7 +994,7 @@ void Sweep::read_field(int field, double *out) {
     CUDA_CHECK(cudaGetLastError());
     // out == NULL: a worker rank of a sharded job takes part in the field's collective but keeps no host copy
     if (out) CUDA_CHECK(cudaMemcpyAsync(out, srcp, sizeof(double) * N, cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (wait) CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
 }  // namespace ssw
@@ -1104,6 +1104,22 @@ int ssw_read(ssw_handle *h, ssw_field field, double *out) {
     if (!out && h->s.P.world_size <= 1) ssw::fail(SSW_E_INVALID, "null out pointer");
     h->s.read_field((int)field, out);
     h->s.resolve_timers();
+    SSW_CATCH
+}
+
+int ssw_read_begin(ssw_handle *h, ssw_field field, double *out) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    if (!out && h->s.P.world_size <= 1) ssw::fail(SSW_E_INVALID, "null out pointer");
+    h->s.read_field((int)field, out, /*wait=*/false);
+    SSW_CATCH
+}
+
+int ssw_sync(ssw_handle *h) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    CUDA_CHECK(cudaSetDevice(h->s.device));
+    h->s.resolve_timers();   // synchronises the stream
     SSW_CATCH
 }
 

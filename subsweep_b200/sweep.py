@@ -248,6 +248,13 @@ class Sweep:
         self._check(self.lib.ssw_read(self._h, capi.FIELDS[field_name], capi.dptr(out)))
         return out
 
+    def read_begin(self, field_name: str, out: Optional[np.ndarray]) -> None:
+        """Queue the read-back of a field (``out`` pinned host memory; None on a worker rank); valid after sync()."""
+        self._check(self.lib.ssw_read_begin(self._h, capi.FIELDS[field_name], None if out is None else capi.dptr(out)))
+
+    def sync(self) -> None:
+        self._check(self.lib.ssw_sync(self._h))
+
     def read_as_worker(self, field_name: str) -> None:
         """Worker rank of a sharded job: take part in the field's collective, copy nothing (ssw_read with NULL)."""
         self._check(self.lib.ssw_read(self._h, capi.FIELDS[field_name], None))

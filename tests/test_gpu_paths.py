@@ -59,3 +59,18 @@ def test_sweep_plugin_surface(cuda_lib):
     ionized = comps["ionized_hydrogen_fraction"] > 0.5
     assert ionized.any()
     assert np.all(np.isfinite(comps["ionization_time"][ionized])) and np.all(np.isposinf(comps["ionization_time"][~ionized]))
+
+
+def test_queued_read_back_equals_blocking_read(cuda_lib):
+    """ssw_read_begin + ssw_sync (the five-component write-back with one synchronisation) against ssw_read."""
+    params, g, f = make_problem("cartesian", 8, True, n_dirs=16, n_levels=2)
+    s = Sweep(params, g, **f)
+    for _ in range(3):
+        s.run_sweeps()
+    names = ("ionized_hydrogen_fraction", "temperature", "timestep", "photon_rate", "ionization_time")
+    queued = {k: np.full(g.n_cells, np.nan) for k in names}
+    for k in names:
+        s.read_begin(k, queued[k])
+    s.sync()
+    for k in names:
+        assert np.array_equal(queued[k], s.read(k), equal_nan=True), k
