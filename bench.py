@@ -423,7 +423,8 @@ def run_b200(args) -> None:
     # measured DRAM traffic of the same kernel on the same workload, from the committed ncu --set full capture
     traffic, traffic_source = None, None
     tfile = ROOT / "profiles" / "roofline_traffic.json"
-    if tfile.exists() and world == 1 and (args.n, args.grid, args.dirs, args.workload) == (128, "cartesian", 84, "box"):
+    if tfile.exists() and world == 1 and (args.n, args.grid, args.dirs, args.workload) == (128, "cartesian", 84, "box") \
+            and sweep.stat("patch_macro_tiles") > 0:
         t = json.loads(tfile.read_text())
         traffic, traffic_source = t["dram_bytes_per_launch"], t["source"]
     roofline = {
