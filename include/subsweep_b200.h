@@ -256,6 +256,18 @@ int ssw_reset_timings(ssw_handle *h);
 /* contiguous direction shard [begin, end) of rank `rank` out of `world_size` */
 int ssw_direction_shard(int32_t n_dirs, int32_t world_size, int32_t rank, int32_t *begin,
                         int32_t *end);
+/* host-side pieces of the patch-ordered sweep, exposed for tests; no device needed.
+ * ssw_patch_lattice: patch index of every cell for boxes of about target_cells cells; returns the number of
+ * patches (0: no lattice qualifies, < 0: error).  ssw_direction_groups: directions of one octant (sign pattern),
+ * at most max_per_group per group; returns the number of groups. */
+int32_t ssw_patch_lattice(const double *xyz /* N x 3 */, uint64_t n_cells, int32_t target_cells,
+                          uint32_t *patch_of /* N */);
+int32_t ssw_direction_groups(const double *dirs_xyz /* D x 3 */, int32_t n_dirs, int32_t max_per_group,
+                             int32_t *group_of /* D */);
+/* ssw_patch_levels: level of every macro-tile from the quotient graph; upwind[(g * P + p) * 32 ..] lists the upwind
+ * patches of patch p for group g, terminated by 0xffffffff.  Returns the number of levels, SSW_E_DEADLOCK if a
+ * group's graph has a cycle (the grid then keeps the level-barrier stream). */
+int32_t ssw_patch_levels(const uint32_t *upwind, int32_t n_groups, int32_t n_patches, uint32_t *level_out /* G x P */);
 /* TimestepLevel::from_max_timestep_and_desired_timestep (src/sweep/timestep_level.rs:27-36),
  * host-side scalar version of the device rule */
 int32_t ssw_level_from_timesteps(int32_t max_num_levels, double max_timestep, double desired);

@@ -107,6 +107,9 @@ SYMBOLS = {
     "ssw_get_timings": (C.c_int, [H, C.POINTER(Timings)]),
     "ssw_reset_timings": (C.c_int, [H]),
     "ssw_direction_shard": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ssw_patch_lattice": (C.c_int32, [c_double_p, C.c_uint64, C.c_int32, C.POINTER(C.c_uint32)]),
+    "ssw_direction_groups": (C.c_int32, [c_double_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "ssw_patch_levels": (C.c_int32, [C.POINTER(C.c_uint32), C.c_int32, C.c_int32, C.POINTER(C.c_uint32)]),
     "ssw_level_from_timesteps": (C.c_int32, [C.c_int32, C.c_double, C.c_double]),
     "ssw_levels_in_sweep_order": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32]),
     "ssw_chemistry_batch": (C.c_int, [C.c_int32, C.c_uint64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,

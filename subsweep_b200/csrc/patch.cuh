@@ -696,6 +696,51 @@ inline uint32_t make_direction_groups(const double *dirs_local, uint32_t n_dl, u
     return G;
 }
 
+// Levels of the macro-tiles: Kahn's algorithm over the quotient graph of every group.  dep[(grp * P + p) * 32 ..] lists
+// the upwind patches of patch p (kEmptyDep-terminated).  level = 1 + max level of the upwind macro-tiles (0: none).
+// Returns false if some group's graph has a cycle.  Pure host code (also behind ssw_patch_levels for the CPU tests).
+inline bool level_macro_tiles(const unsigned int *dep, uint32_t G, uint32_t P, std::vector<uint32_t> &mt_level,
+                              std::vector<uint32_t> &ndep, uint32_t &max_level) {
+    mt_level.assign((size_t)G * P, 0);
+    ndep.assign((size_t)G * P, 0);
+    max_level = 0;
+    for (uint32_t grp = 0; grp < G; ++grp) {
+        std::vector<uint32_t> indeg(P, 0), succ_off(P + 1, 0), succ, order;
+        for (uint32_t p = 0; p < P; ++p) {
+            const unsigned int *row = dep + ((size_t)grp * P + p) * kMaxPatchDeps;
+            uint32_t k = 0;
+            while (k < kMaxPatchDeps && row[k] != kEmptyDep) {
+                if (row[k] >= P) return false;
+                succ_off[row[k] + 1]++;
+                ++k;
+            }
+            indeg[p] = k;
+            ndep[(size_t)grp * P + p] = k;
+        }
+        for (uint32_t p = 0; p < P; ++p) succ_off[p + 1] += succ_off[p];
+        succ.resize(succ_off[P]);
+        std::vector<uint32_t> cur(succ_off.begin(), succ_off.end() - 1);
+        for (uint32_t p = 0; p < P; ++p) {
+            const unsigned int *row = dep + ((size_t)grp * P + p) * kMaxPatchDeps;
+            for (uint32_t k = 0; k < indeg[p]; ++k) succ[cur[row[k]]++] = p;
+        }
+        order.reserve(P);
+        for (uint32_t p = 0; p < P; ++p) if (indeg[p] == 0) order.push_back(p);
+        for (size_t i = 0; i < order.size(); ++i) {
+            const uint32_t p = order[i];
+            for (uint32_t j = succ_off[p]; j < succ_off[p + 1]; ++j) {
+                const uint32_t q = succ[j];
+                uint32_t &lv = mt_level[(size_t)grp * P + q];
+                lv = std::max(lv, mt_level[(size_t)grp * P + p] + 1);
+                if (--indeg[q] == 0) order.push_back(q);
+            }
+        }
+        if (order.size() != P) return false;
+        for (uint32_t p = 0; p < P; ++p) max_level = std::max(max_level, mt_level[(size_t)grp * P + p]);
+    }
+    return true;
+}
+
 // Builds the patch-ordered schedule from the level-sorted task list of the all-cells sweep.  Throws
 // PatchUnsupported when the grid does not admit the form (the caller falls back to compile_schedule).
 inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGrid &pg, const double *dirs_local,
@@ -749,38 +794,10 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
             cuda_ok(cudaMemcpy(po.data(), pg.patch_off, sizeof(uint32_t) * ((size_t)P + 1), cudaMemcpyDeviceToHost), "copy patch_off");
             for (uint32_t p = 0; p < P; ++p) patch_size[p] = po[p + 1] - po[p];
         }
-        std::vector<uint32_t> mt_level((size_t)G * P, 0), ndep((size_t)G * P, 0);
+        std::vector<uint32_t> mt_level, ndep;
         uint32_t max_level = 0;
-        for (uint32_t grp = 0; grp < G; ++grp) {
-            std::vector<uint32_t> indeg(P, 0), succ_off(P + 1, 0), succ, order;
-            for (uint32_t p = 0; p < P; ++p) {
-                const unsigned int *row = dep_h.data() + ((size_t)grp * P + p) * kMaxPatchDeps;
-                uint32_t k = 0;
-                while (k < kMaxPatchDeps && row[k] != kEmptyDep) { succ_off[row[k] + 1]++; ++k; }
-                indeg[p] = k;
-                ndep[(size_t)grp * P + p] = k;
-            }
-            for (uint32_t p = 0; p < P; ++p) succ_off[p + 1] += succ_off[p];
-            succ.resize(succ_off[P]);
-            std::vector<uint32_t> cur(succ_off.begin(), succ_off.end() - 1);
-            for (uint32_t p = 0; p < P; ++p) {
-                const unsigned int *row = dep_h.data() + ((size_t)grp * P + p) * kMaxPatchDeps;
-                for (uint32_t k = 0; k < indeg[p]; ++k) succ[cur[row[k]]++] = p;
-            }
-            order.reserve(P);
-            for (uint32_t p = 0; p < P; ++p) if (indeg[p] == 0) order.push_back(p);
-            for (size_t i = 0; i < order.size(); ++i) {
-                const uint32_t p = order[i];
-                for (uint32_t j = succ_off[p]; j < succ_off[p + 1]; ++j) {
-                    const uint32_t q = succ[j];
-                    uint32_t &lv = mt_level[(size_t)grp * P + q];
-                    lv = std::max(lv, mt_level[(size_t)grp * P + p] + 1);
-                    if (--indeg[q] == 0) order.push_back(q);
-                }
-            }
-            if (order.size() != P) throw PatchUnsupported("patches depend on each other cyclically for a direction group");
-            for (uint32_t p = 0; p < P; ++p) max_level = std::max(max_level, mt_level[(size_t)grp * P + p]);
-        }
+        if (!level_macro_tiles(dep_h.data(), G, P, mt_level, ndep, max_level))
+            throw PatchUnsupported("patches depend on each other cyclically for a direction group");
         std::vector<uint32_t> mt_list;   // grp * P + p of every non-empty macro-tile, in rank order
         mt_list.reserve((size_t)G * P);
         for (uint32_t grp = 0; grp < G; ++grp)

@@ -471,11 +471,12 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
 
 // Cell centres -> spatial patches: boxes of a regular lattice over the bounding box of the centres, sized for
 // about SSW_PATCH_CELLS (512) cells each.  Host preprocessing, once per grid.
-void Sweep::set_positions(const double *xyz) {
-    if (!xyz) fail(SSW_E_INVALID, "null positions");
-    have_patches = false;
-    patch_note.clear();
-    if (state) fail(SSW_E_INVALID, "cell positions must be set before the first all-cells schedule is compiled");
+// Cell centres -> spatial patches: boxes of a regular lattice over the bounding box of the centres, sized for about
+// `target` cells each (halved until no patch exceeds kMaxPatchCells).  Pure host code (also behind ssw_patch_lattice
+// for the CPU tests).  Returns the number of patches, 0 if no lattice qualifies (`why` says why).
+static uint32_t build_patch_lattice(const double *xyz, uint32_t N, double target, std::vector<uint32_t> &pof,
+                                    std::vector<uint32_t> &poff, std::vector<uint32_t> &pcl, std::vector<uint16_t> &lidx,
+                                    uint32_t &max_cells, std::string &why) {
     double lo[3], hi[3];
     for (int k = 0; k < 3; ++k) { lo[k] = std::numeric_limits<double>::infinity(); hi[k] = -lo[k]; }
     for (uint32_t c = 0; c < N; ++c)
@@ -489,13 +490,10 @@ void Sweep::set_positions(const double *xyz) {
     double vol = 1.0;
     for (int k = 0; k < 3; ++k)
         if (hi[k] > lo[k]) { ++dims; vol *= hi[k] - lo[k]; }
-    // patch size: a direction shard (few local directions) is bound by the chain of dependent macro-tiles -> large
-    // patches (8^3), few levels; with many directions the sweep is throughput-bound and small patches (5^3) keep
-    // more macro-tiles resident per SM (measured on B200, DESIGN.md section 5.3)
-    double target = (double)stream_env_u32("SSW_PATCH_CELLS", Dl <= 24 ? 512 : 125);
     target = std::min<double>(std::max<double>(target, 8.0), (double)kMaxPatchCells);
-    std::vector<uint32_t> pof(N), poff, pcl(N);
-    std::vector<uint16_t> lidx(N);
+    pof.assign(N, 0);
+    pcl.assign(N, 0);
+    lidx.assign(N, 0);
     for (int attempt = 0; attempt < 8; ++attempt, target *= 0.5) {
         uint32_t nbx[3] = {1, 1, 1};
         double org[3] = {lo[0], lo[1], lo[2]}, width[3] = {1.0, 1.0, 1.0};
@@ -514,16 +512,16 @@ void Sweep::set_positions(const double *xyz) {
             }
         }
         const uint64_t P64 = (uint64_t)nbx[0] * nbx[1] * nbx[2];
-        if (P64 > (1u << 20)) { patch_note = "more than 2^20 patches"; return; }
+        if (P64 > (1u << 20)) { why = "more than 2^20 patches"; return 0; }
         const uint32_t Pn = (uint32_t)P64;
         std::vector<uint32_t> count(Pn, 0);
         for (uint32_t c = 0; c < N; ++c) {
-            uint32_t b[3];
+            uint32_t bx[3];
             for (int k = 0; k < 3; ++k) {
                 const double t = (xyz[3 * (size_t)c + k] - org[k]) / width[k];
-                b[k] = (uint32_t)std::min<double>((double)nbx[k] - 1.0, std::max<double>(0.0, std::floor(t)));
+                bx[k] = (uint32_t)std::min<double>((double)nbx[k] - 1.0, std::max<double>(0.0, std::floor(t)));
             }
-            pof[c] = (b[0] * nbx[1] + b[1]) * nbx[2] + b[2];
+            pof[c] = (bx[0] * nbx[1] + bx[1]) * nbx[2] + bx[2];
             count[pof[c]]++;
         }
         const uint32_t mx = *std::max_element(count.begin(), count.end());
@@ -531,23 +529,41 @@ void Sweep::set_positions(const double *xyz) {
         poff.assign((size_t)Pn + 1, 0);
         for (uint32_t p = 0; p < Pn; ++p) poff[p + 1] = poff[p] + count[p];
         std::vector<uint32_t> cur(poff.begin(), poff.end() - 1);
-        for (uint32_t c = 0; c < N; ++c) {
+        for (uint32_t c = 0; c < N; ++c) {   // ascending cell index inside a patch
             const uint32_t pos = cur[pof[c]]++;
             pcl[pos] = c;
             lidx[c] = (uint16_t)(pos - poff[pof[c]]);
         }
-        CUDA_CHECK(cudaSetDevice(device));
-        patch_of.alloc(N); patch_of.upload(pof.data(), N, stream);
-        patch_lidx.alloc(N); patch_lidx.upload(lidx.data(), N, stream);
-        patch_off.alloc((size_t)Pn + 1); patch_off.upload(poff.data(), (size_t)Pn + 1, stream);
-        patch_cells.alloc(N); patch_cells.upload(pcl.data(), N, stream);
-        CUDA_CHECK(cudaStreamSynchronize(stream));
-        n_patches = Pn;
-        patch_max_cells = mx;
-        have_patches = true;
-        return;
+        max_cells = mx;
+        return Pn;
     }
-    patch_note = "no patch lattice with <= 1024 cells per patch";
+    why = "no patch lattice with <= 1024 cells per patch";
+    return 0;
+}
+
+void Sweep::set_positions(const double *xyz) {
+    if (!xyz) fail(SSW_E_INVALID, "null positions");
+    have_patches = false;
+    patch_note.clear();
+    if (state) fail(SSW_E_INVALID, "cell positions must be set before the first all-cells schedule is compiled");
+    // patch size: a direction shard (few local directions) is bound by the chain of dependent macro-tiles -> large
+    // patches (8^3), few levels; with many directions the sweep is throughput-bound and small patches (5^3) keep
+    // more macro-tiles resident per SM (measured on B200, DESIGN.md section 5.3)
+    const double target = (double)stream_env_u32("SSW_PATCH_CELLS", Dl <= 24 ? 512 : 125);
+    std::vector<uint32_t> pof, poff, pcl;
+    std::vector<uint16_t> lidx;
+    uint32_t mx = 0;
+    const uint32_t Pn = build_patch_lattice(xyz, N, target, pof, poff, pcl, lidx, mx, patch_note);
+    if (!Pn) return;
+    CUDA_CHECK(cudaSetDevice(device));
+    patch_of.alloc(N); patch_of.upload(pof.data(), N, stream);
+    patch_lidx.alloc(N); patch_lidx.upload(lidx.data(), N, stream);
+    patch_off.alloc((size_t)Pn + 1); patch_off.upload(poff.data(), (size_t)Pn + 1, stream);
+    patch_cells.alloc(N); patch_cells.upload(pcl.data(), N, stream);
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    n_patches = Pn;
+    patch_max_cells = mx;
+    have_patches = true;
 }
 
 void Sweep::refresh_histogram() {
@@ -1297,6 +1313,41 @@ int ssw_direction_shard(int32_t n_dirs, int32_t world_size, int32_t rank, int32_
     *begin = (int32_t)((int64_t)n_dirs * rank / world_size);
     *end = (int32_t)((int64_t)n_dirs * (rank + 1) / world_size);
     return SSW_OK;
+}
+
+int32_t ssw_patch_lattice(const double *xyz, uint64_t n_cells, int32_t target_cells, uint32_t *patch_of) {
+    try {
+        if (!xyz || !patch_of || n_cells < 1 || n_cells > 0xfffffff0ull) return SSW_E_INVALID;
+        std::vector<uint32_t> pof, poff, pcl;
+        std::vector<uint16_t> lidx;
+        uint32_t mx = 0;
+        std::string why;
+        const uint32_t Pn = ssw::build_patch_lattice(xyz, (uint32_t)n_cells, (double)target_cells, pof, poff, pcl, lidx, mx, why);
+        if (!Pn) { ssw::g_last_error = why; return 0; }
+        std::copy(pof.begin(), pof.end(), patch_of);
+        return (int32_t)Pn;
+    } catch (const std::exception &e) {
+        ssw::g_last_error = e.what();
+        return SSW_E_INVALID;
+    }
+}
+
+int32_t ssw_patch_levels(const uint32_t *upwind, int32_t n_groups, int32_t n_patches, uint32_t *level_out) {
+    if (!upwind || !level_out || n_groups < 1 || n_patches < 1) return SSW_E_INVALID;
+    std::vector<uint32_t> lvl, ndep;
+    uint32_t max_level = 0;
+    if (!ssw::level_macro_tiles(upwind, (uint32_t)n_groups, (uint32_t)n_patches, lvl, ndep, max_level)) return SSW_E_DEADLOCK;
+    std::copy(lvl.begin(), lvl.end(), level_out);
+    return (int32_t)max_level + 1;
+}
+
+int32_t ssw_direction_groups(const double *dirs_xyz, int32_t n_dirs, int32_t max_per_group, int32_t *group_of) {
+    if (!dirs_xyz || !group_of || n_dirs < 1 || n_dirs > ssw::kMaxDirs || max_per_group < 1) return SSW_E_INVALID;
+    std::vector<uint16_t> grp, rank;
+    std::vector<uint32_t> kd;
+    const uint32_t G = ssw::make_direction_groups(dirs_xyz, (uint32_t)n_dirs, (uint32_t)max_per_group, grp, rank, kd);
+    for (int32_t d = 0; d < n_dirs; ++d) group_of[d] = grp[d];
+    return (int32_t)G;
 }
 
 int32_t ssw_level_from_timesteps(int32_t max_num_levels, double max_timestep, double desired) {

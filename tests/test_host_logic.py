@@ -144,3 +144,86 @@ def test_units():
     assert U.parse_quantity(0.1) == 0.1
     with pytest.raises(ValueError):
         U.parse_quantity("1 parsecs")
+
+
+# ---- host-side pieces of the patch-ordered sweep (patch.cuh / sweep.cu) ----------------
+def _patch_lattice(pos, target):
+    lib = capi.load()
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    out = np.empty(len(pos), dtype=np.uint32)
+    n = lib.ssw_patch_lattice(capi.dptr(pos), len(pos), target, out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return n, out
+
+
+@pytest.mark.parametrize("n,target,per_axis,cells", [(16, 64, 4, 64), (16, 512, 2, 512), (128, 512, 16, 512), (12, 8, 6, 8)])
+def test_patch_lattice_aligns_with_a_cartesian_grid(n, target, per_axis, cells):
+    """Cell centres of a Cartesian grid, boxes of `target` cells: the lattice must coincide with whole blocks of cells."""
+    h = 3.7
+    i, j, k = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    pos = np.stack([(i + 0.5) * h, (j + 0.5) * h, (k + 0.5) * h], axis=-1).reshape(-1, 3)
+    n_patches, patch = _patch_lattice(pos, target)
+    assert n_patches == per_axis ** 3
+    w = n // per_axis
+    expect = ((i // w) * per_axis + (j // w)) * per_axis + (k // w)
+    assert np.array_equal(patch.reshape(n, n, n), expect)
+    assert np.all(np.bincount(patch, minlength=n_patches) == cells)
+
+
+def test_patch_lattice_on_scattered_points_and_degenerate_axes():
+    rng = np.random.default_rng(7)
+    pos = rng.uniform(0.0, 1.0, size=(20000, 3))
+    n_patches, patch = _patch_lattice(pos, 125)
+    counts = np.bincount(patch, minlength=n_patches)
+    assert n_patches > 1 and counts.sum() == len(pos) and counts.max() <= 1024
+    assert 60 < counts.mean() < 250                       # about the requested size
+    # neighbouring points land in the same or an adjacent box: boxes are spatially compact
+    flat = pos.copy()
+    flat[:, 2] = 0.25                                     # a plane: one box along the degenerate axis
+    n2, patch2 = _patch_lattice(flat, 100)
+    assert n2 > 1 and np.bincount(patch2, minlength=n2).max() <= 1024
+    n1, patch1 = _patch_lattice(np.zeros((1, 3)), 512)    # a single cell
+    assert n1 == 1 and patch1[0] == 0
+
+
+@pytest.mark.parametrize("kd", [1, 3, 6, 11, 32])
+def test_direction_groups_follow_the_octants(kd):
+    lib = capi.load()
+    d = Directions.from_num(84).xyz
+    grp = np.empty(84, dtype=np.int32)
+    n_groups = lib.ssw_direction_groups(capi.dptr(d), 84, kd, grp.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert n_groups >= 1 and grp.min() == 0 and grp.max() == n_groups - 1
+    sign = np.sign(d).astype(np.int64)
+    for g in range(n_groups):
+        members = np.flatnonzero(grp == g)
+        assert 1 <= len(members) <= kd
+        assert len({tuple(s) for s in sign[members]}) == 1          # one sign pattern per group: one dependency DAG
+    # as few groups as the octants allow
+    classes = {}
+    for s in map(tuple, sign):
+        classes[s] = classes.get(s, 0) + 1
+    assert n_groups == sum(-(-c // kd) for c in classes.values())
+
+
+def test_patch_levels_kahn_over_the_quotient_graph():
+    lib = capi.load()
+    n, empty = 4, 0xFFFFFFFF
+    P = n ** 3
+    dep = np.full((2, P, 32), empty, dtype=np.uint32)
+    idx = lambda i, j, k: (i * n + j) * n + k   # noqa: E731
+    for i in range(n):
+        for j in range(n):
+            for k in range(n):
+                up0 = [idx(a, b, c) for a, b, c in ((i - 1, j, k), (i, j - 1, k), (i, j, k - 1)) if min(a, b, c) >= 0]
+                up1 = [idx(a, b, c) for a, b, c in ((i + 1, j, k), (i, j, k - 1)) if 0 <= a < n and c >= 0]
+                dep[0, idx(i, j, k), :len(up0)] = up0       # octant (+,+,+)
+                dep[1, idx(i, j, k), :len(up1)] = up1       # a direction with d_y = 0, d_x < 0
+    lvl = np.empty((2, P), dtype=np.uint32)
+    n_levels = lib.ssw_patch_levels(dep.ctypes.data_as(C.POINTER(C.c_uint32)), 2, P, lvl.ctypes.data_as(C.POINTER(C.c_uint32)))
+    i, j, k = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    assert n_levels == 3 * (n - 1) + 1
+    assert np.array_equal(lvl[0].reshape(n, n, n), i + j + k)
+    assert np.array_equal(lvl[1].reshape(n, n, n), (n - 1 - i) + k)
+    # two patches that are upwind of each other (a jagged Voronoi patch boundary): no patch form
+    dep[1, idx(0, 0, 0), 0] = idx(0, 0, 1)
+    dep[1, idx(0, 0, 1), :2] = [idx(1, 0, 1), idx(0, 0, 0)]
+    assert lib.ssw_patch_levels(dep.ctypes.data_as(C.POINTER(C.c_uint32)), 2, P, lvl.ctypes.data_as(C.POINTER(C.c_uint32))) == capi.SSW_E_DEADLOCK
