@@ -24,9 +24,10 @@
 //   * everything a block needs is, as in stream.cuh, ONE sequential byte stream per block
 //     (macro-tile head packet, then one tile packet per <= THREADS slots of a sub-level), prefetched
 //     with TMA bulk copies into a shared-memory ring.
-//   * per-cell photon rate: sum_d incoming[d] (src/sweep/mod.rs:554-558) is reduced per (cell,
-//     sub-level) segment with warp shuffles, accumulated per patch cell in shared memory and stored
-//     once per (group, cell): no atomics, no read-modify-write in global memory.
+//   * per-cell photon rate: a task writes its incoming rate into a shared-memory row [patch cell][direction of the
+//     group]; when the macro-tile is done one thread per cell sums its row in direction order (sum_d incoming[d],
+//     src/sweep/mod.rs:554-558) and stores it once per (group, cell): no atomics, no read-modify-write in global
+//     memory, and nothing of the reduction sits on the dependent chain of the tiles.
 //   * periodic faces never carry a dependency (src/sweep/mod.rs:505-513): every periodic entry reads
 //     a snapshot of its donor taken before the sweep (the lag of DESIGN.md section 4); the
 //     periodic_source term of the rate (donors' NEW rates, site.rs:53-56) is one small kernel after
@@ -458,7 +459,7 @@ struct PatchArgs {
     double threshold;
     uint32_t stages, stage_bytes, vmax, pc_max, smax;
     uint32_t n_cells, epoch, poll_ns;
-    unsigned long long *prof; // optional per-block cycles {total, dependency poll, packet wait, packets}
+    unsigned long long *prof; // optional per-block cycle counters, 10 per block (SSW_STREAM_PROFILE)
 };
 
 template <int THREADS, int MIN_BLOCKS, bool PROFILE>
@@ -499,7 +500,7 @@ patch_sweep_kernel(PatchArgs a) {
     }
     uint32_t gslot0 = 0, n_slots = 0, group = 0, rank = 0, n_cells = 0, kdg = 1;
     uint32_t stage = 0, parity = 0;
-    long long t_begin = 0, t_poll = 0, t_pkt = 0, tp = 0, t_cmp = 0, t_scan = 0, t_bar = 0, t_post = 0, t_head = 0, tq = 0;
+    long long t_begin = 0, t_poll = 0, t_pkt = 0, tp = 0, t_cmp = 0, t_bar = 0, t_post = 0, t_head = 0, tq = 0;
     if (PROFILE && tid == 0) t_begin = clock64();
     for (uint32_t k = 0; k < n_my; ++k) {
         if (PROFILE && tid == 0) tp = clock64();
@@ -634,7 +635,6 @@ patch_sweep_kernel(PatchArgs a) {
         a.prof[10 * blockIdx.x + 2] = (unsigned long long)t_pkt;
         a.prof[10 * blockIdx.x + 3] = n_my;
         a.prof[10 * blockIdx.x + 4] = (unsigned long long)t_cmp;
-        a.prof[10 * blockIdx.x + 5] = (unsigned long long)t_scan;
         a.prof[10 * blockIdx.x + 6] = (unsigned long long)t_bar;
         a.prof[10 * blockIdx.x + 7] = (unsigned long long)t_post;
         a.prof[10 * blockIdx.x + 8] = (unsigned long long)t_head;
@@ -1171,10 +1171,10 @@ inline void run_patch(Compiled &C, const double2 *cellrec, double threshold, cud
         cudaMemcpyAsync(h.data(), prof_dev, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, stream);
         cudaStreamSynchronize(stream);
         cudaFree(prof_dev);
-        double tot = 0, poll = 0, pkt = 0, packets = 0, tmax = 0, cmp = 0, scan = 0, bar = 0, post = 0, head = 0;
+        double tot = 0, poll = 0, pkt = 0, packets = 0, tmax = 0, cmp = 0, bar = 0, post = 0, head = 0;
         for (uint32_t b = 0; b < C.n_blocks; ++b) {
             tot += (double)h[10 * b]; poll += (double)h[10 * b + 1]; pkt += (double)h[10 * b + 2]; packets += (double)h[10 * b + 3];
-            cmp += (double)h[10 * b + 4]; scan += (double)h[10 * b + 5]; bar += (double)h[10 * b + 6]; post += (double)h[10 * b + 7];
+            cmp += (double)h[10 * b + 4]; bar += (double)h[10 * b + 6]; post += (double)h[10 * b + 7];
             head += (double)h[10 * b + 8];
             tmax = std::max(tmax, (double)h[10 * b]);
         }
