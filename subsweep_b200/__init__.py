@@ -6,6 +6,8 @@ The product is ``lib/libsubsweep_b200.so`` (hand-written CUDA behind the C ABI o
 * :mod:`subsweep_b200.capi`   ctypes binding (twin of the Rust FFI crate in INTEGRATION.md)
 * :mod:`subsweep_b200.sweep`  ``SweepParameters`` / ``Directions`` / ``Sweep`` / ``SweepPlugin``
 * :mod:`subsweep_b200.grid`   flat-grid producers (Cartesian, Voronoi via Qhull) -- host preprocessing
+* :mod:`subsweep_b200.snapshot`  snapshot output of the per-particle components (names, units, layout of the reference)
+* :mod:`subsweep_b200.distributed`  NCCL hooks for direction sharding (all-reduce, reduce-scatter / all-gather)
 * :mod:`subsweep_b200.build`  nvcc build of the library
 """
 from .grid import FlatGrid  # noqa: F401
