@@ -50,7 +50,7 @@ struct CellView {
 };
 
 // Flux state access.  Before the all-cells schedule is compiled the state is q = out / ttot in
-// the natural [dl][c] layout; afterwards it is out_slot (compiled.cuh) reached through slot_of.
+// the natural [dl][c] layout; afterwards it is out_slot (patch.cuh / stream.cuh) reached through slot_of.
 struct StateView {
     double *q;
     const uint32_t *slot_of;

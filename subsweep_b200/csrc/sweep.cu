@@ -2,7 +2,7 @@
 // Sweep<HydrogenOnly> (src/sweep/mod.rs:172-610) and the C ABI of include/subsweep_b200.h.
 //
 // There is no CPU fallback in this file: every path launches the kernels of kernels.cuh /
-// compiled.cuh on the CUDA device and fails with SSW_E_CUDA when that is impossible.
+// patch.cuh / stream.cuh on the CUDA device and fails with SSW_E_CUDA when that is impossible.
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 
@@ -164,7 +164,7 @@ struct Sweep {
     uint64_t levels_version = 1;
 
     std::vector<std::unique_ptr<Schedule>> sched;  // [0..L-1] partial sets by current level, [L] all cells
-    Compiled *state = nullptr;  // non-null once the flux state lives in slot order (compiled.cuh)
+    Compiled *state = nullptr;  // non-null once the flux state lives in slot order (patch.cuh / stream.cuh)
 
     ssw_allreduce_fn allreduce = nullptr;
     void *allreduce_ctx = nullptr;
