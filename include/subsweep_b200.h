@@ -226,7 +226,8 @@ typedef enum ssw_stat {
     SSW_STAT_CHEM_ATTEMPTS = 8,     /* try_timestep_update calls                                 */
     SSW_STAT_CHEM_MAX_DEPTH = 9,
     SSW_STAT_PATCH_MACRO_TILES = 10, /* macro-tiles of the patch-ordered all-cells sweep (0: not in use) */
-    SSW_STAT_PATCH_LEVELS = 11       /* dependent macro-tile levels (vs SSW_STAT_WAVEFRONT_LEVELS)       */
+    SSW_STAT_PATCH_LEVELS = 11,      /* dependent macro-tile levels (vs SSW_STAT_WAVEFRONT_LEVELS)       */
+    SSW_STAT_PATCH_PHASES = 12       /* phases of the macro-tiles (1: the patch graph was acyclic)       */
 } ssw_stat;
 int ssw_get_stat(ssw_handle *h, ssw_stat which, uint64_t *out);
 

@@ -70,6 +70,7 @@ struct PatchGrid {   // device view of the cell -> patch map
     const uint32_t *patch_cells;  // N, patch-major, ascending cell index inside a patch
     uint32_t n_patches;
     uint32_t max_cells;
+    uint32_t dims[3];             // boxes per axis: patch = (bx * dims[1] + by) * dims[2] + bz
 };
 
 // packet descriptor, block-major, in consumption order
@@ -181,6 +182,104 @@ p_edges_kernel(GridView g, uint32_t n_dl, const uint32_t *__restrict__ patch_of,
     }
 }
 
+// ---- phases: the patch form for grids whose patch graph is cyclic (Voronoi) ----------------------------------------
+// pi[grp * P + p] is a total order of the patches of a group.  A dependency edge is "back" if it runs from a later to
+// an earlier patch; phase(task) = max over its upwind tasks of (their phase + [edge is back]).  Macro-tiles
+// (patch, group, phase) ordered by (phase, pi) are a topological order of their quotient graph by construction.
+// One launch per wavefront level, in level order (the upwind tasks of a level are final).
+__global__ void __launch_bounds__(256)
+p_phase_kernel(GridView g, const uint32_t *__restrict__ tasks, uint32_t s0, uint32_t s1, const uint32_t *__restrict__ patch_of,
+               const uint16_t *__restrict__ group_of, uint32_t n_patches, const uint32_t *__restrict__ pi,
+               uint8_t *phase, unsigned int *counters) {
+    const uint32_t i = s0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s1) return;
+    const uint32_t t = tasks[i];
+    const uint32_t N = g.n_cells;
+    const uint32_t dl = t / N, c = t - dl * N;
+    const uint32_t *const pig = pi + (size_t)group_of[dl] * n_patches;
+    const uint32_t my_pi = pig[patch_of[c]];
+    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    uint32_t ph = 0;
+    for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
+        if (g.face_kind[f] != 0) continue;
+        if (!(dot_dir(ld_geo(g.face_geo + f), dx, dy, dz) < 0.0)) continue;
+        const uint32_t nb = (uint32_t)g.face_nb[f];
+        const uint32_t q = (uint32_t)phase[(size_t)dl * N + nb] + (pig[patch_of[nb]] > my_pi ? 1u : 0u);
+        ph = max(ph, q);
+    }
+    if (ph > 254u) { atomicExch(counters + 7, 1u); ph = 254u; }
+    phase[t] = (uint8_t)ph;
+    atomicMax(counters + 6, ph);
+}
+
+// which (group, patch, phase) triples exist
+__global__ void __launch_bounds__(256)
+p_present_kernel(uint32_t n_cells, uint32_t n_dl, const uint32_t *__restrict__ patch_of, const uint16_t *__restrict__ group_of,
+                 uint32_t n_patches, uint32_t n_phase, const uint8_t *__restrict__ phase, uint32_t *__restrict__ present) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n_cells * n_dl) return;
+    const uint32_t dl = (uint32_t)(t / n_cells), c = (uint32_t)(t - (size_t)dl * n_cells);
+    present[((size_t)group_of[dl] * n_patches + patch_of[c]) * n_phase + phase[t]] = 1u;
+}
+
+// dense macro-tile ids from the exclusive scan of `present`; mt_key[id] = (group * P + patch) * n_phase + phase
+__global__ void __launch_bounds__(256)
+p_mtid_kernel(const uint32_t *__restrict__ present, const uint32_t *__restrict__ scan, uint32_t n_keys,
+              uint32_t *__restrict__ mtid_of, uint32_t *__restrict__ mt_key) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_keys) return;
+    if (present[k]) { mtid_of[k] = scan[k]; mt_key[scan[k]] = k; }
+    else mtid_of[k] = 0xffffffffu;
+}
+
+// quotient graph over macro-tiles with phases: dep_tab[id * 32 ..] = upwind macro-tiles; smallest wavefront level of
+// every (macro-tile, direction of the group)
+__global__ void __launch_bounds__(256)
+p_edges2_kernel(GridView g, uint32_t n_dl, const uint32_t *__restrict__ patch_of, const uint16_t *__restrict__ group_of,
+                const uint16_t *__restrict__ group_rank, uint32_t n_patches, uint32_t n_phase, uint32_t kd_max,
+                const uint8_t *__restrict__ phase, const uint32_t *__restrict__ mtid_of, const uint32_t *__restrict__ tlevel,
+                unsigned int *dep_tab, unsigned int *minlev, unsigned int *err) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t N = g.n_cells;
+    if (t >= (size_t)N * n_dl) return;
+    const uint32_t dl = (uint32_t)(t / N), c = (uint32_t)(t - (size_t)dl * N);
+    const size_t gbase = (size_t)group_of[dl] * n_patches;
+    const uint32_t me = mtid_of[(gbase + patch_of[c]) * n_phase + phase[t]];
+    atomicMin(minlev + (size_t)me * kd_max + group_rank[dl], tlevel[t]);
+    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    unsigned int *row = dep_tab + (size_t)me * kMaxPatchDeps;
+    for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
+        if (g.face_kind[f] != 0) continue;
+        if (!(dot_dir(ld_geo(g.face_geo + f), dx, dy, dz) < 0.0)) continue;
+        const uint32_t nb = (uint32_t)g.face_nb[f];
+        const uint32_t up = mtid_of[(gbase + patch_of[nb]) * n_phase + phase[(size_t)dl * N + nb]];
+        if (up == me) continue;
+        bool done = false;
+        for (uint32_t i = 0; i < kMaxPatchDeps && !done; ++i) {
+            unsigned int v = *((volatile unsigned int *)(row + i));
+            if (v == kEmptyDep) v = atomicCAS(row + i, kEmptyDep, up);
+            done = v == up || v == kEmptyDep;
+        }
+        if (!done) atomicExch(err, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+p_key2_kernel(uint32_t n_cells, uint32_t n_dl, const uint32_t *__restrict__ patch_of, const uint16_t *__restrict__ group_of,
+              const uint16_t *__restrict__ group_rank, uint32_t n_patches, uint32_t n_phase, uint32_t kd_max,
+              const uint8_t *__restrict__ phase, const uint32_t *__restrict__ mtid_of, const uint32_t *__restrict__ rank_of,
+              const uint32_t *__restrict__ tlevel, const unsigned int *__restrict__ minlev,
+              unsigned long long *__restrict__ keys, unsigned int *err) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n_cells * n_dl) return;
+    const uint32_t dl = (uint32_t)(t / n_cells), c = (uint32_t)(t - (size_t)dl * n_cells);
+    const uint32_t me = mtid_of[((size_t)group_of[dl] * n_patches + patch_of[c]) * n_phase + phase[t]];
+    uint32_t sub = tlevel[t] - minlev[(size_t)me * kd_max + group_rank[dl]];
+    if (sub >= kMaxSub) { atomicExch(err, 1u); sub = kMaxSub - 1; }
+    keys[t] = ((unsigned long long)rank_of[me] << kRankShift) | ((unsigned long long)sub << kSubShift) |
+              (unsigned long long)(c * n_dl + dl);
+}
+
 __global__ void __launch_bounds__(256)
 p_key_kernel(uint32_t n_cells, uint32_t n_dl, const uint32_t *__restrict__ patch_of, const uint16_t *__restrict__ group_of,
              uint32_t n_patches, const uint32_t *__restrict__ rank_of, const uint32_t *__restrict__ tlevel,
@@ -220,13 +319,14 @@ p_pl_rank_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__
 // total downwind effective area; counters[0] += periodic entries, counters[2] = error (> 255 periodic faces)
 __global__ void __launch_bounds__(256)
 p_count_kernel(GridView g, const uint32_t *__restrict__ k32, uint32_t n, uint32_t n_dl,
-               const uint32_t *__restrict__ patch_of, uint32_t *__restrict__ cnt_e, uint32_t *__restrict__ cnt_x,
-               double *__restrict__ ttot_slot, unsigned int *counters) {
+               const uint32_t *__restrict__ patch_of, const uint8_t *__restrict__ phase, uint32_t *__restrict__ cnt_e,
+               uint32_t *__restrict__ cnt_x, double *__restrict__ ttot_slot, unsigned int *counters) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const uint32_t k = k32[s];
     const uint32_t c = k / n_dl, dl = k - c * n_dl;
     const uint32_t pc = patch_of[c];
+    const uint8_t *const ph = phase ? phase + (size_t)dl * g.n_cells : nullptr;   // phases of this direction's tasks
     const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
     uint32_t m = 0, x = 0, np = 0;
     double ttot = 0.0;
@@ -237,7 +337,8 @@ p_count_kernel(GridView g, const uint32_t *__restrict__ k32, uint32_t n, uint32_
         if (d < 0.0) {
             if (kind == 0) {
                 ++m;
-                if (patch_of[(uint32_t)g.face_nb[f]] != pc) ++x;
+                const uint32_t nb = (uint32_t)g.face_nb[f];
+                if (patch_of[nb] != pc || (ph && ph[nb] != ph[c])) ++x;   // not the same macro-tile: external
             } else if (kind == 2) {
                 ++m; ++x; ++np;
             }
@@ -277,6 +378,9 @@ struct PFillArgs {
     const uint64_t *head_off;     // n_mt: byte offset of the macro-tile's head packet in the stream
     const unsigned int *dep_tab;
     const uint32_t *rank_of;
+    const uint32_t *mt_row;       // n_mt: row of the macro-tile in dep_tab
+    const uint32_t *dep_base;     // n_mt: added to a dep_tab entry before the rank_of lookup
+    const uint8_t *phase;         // per task (dl * N + c), or null: no phases
     uint32_t *lag_src;
     unsigned int *counters;       // [1] lag cursor, [3] ordering violations
 };
@@ -306,10 +410,10 @@ p_fill_kernel(PFillArgs a) {
         uint32_t *dep = reinterpret_cast<uint32_t *>(pkt + L.dep);
         uint32_t *ext = reinterpret_cast<uint32_t *>(pkt + L.ext);
         uint32_t *cells = reinterpret_cast<uint32_t *>(pkt + L.cells);
-        const unsigned int *row = a.dep_tab + ((size_t)grp * a.pg.n_patches + p) * kMaxPatchDeps;
+        const unsigned int *row = a.dep_tab + (size_t)a.mt_row[r] * kMaxPatchDeps;
         const uint32_t dep_pad = align16(4u * n_dep) / 4u;
         for (uint32_t i = tid; i < dep_pad; i += blockDim.x)
-            dep[i] = i < n_dep ? a.rank_of[(size_t)grp * a.pg.n_patches + row[i]] : 0u;
+            dep[i] = i < n_dep ? a.rank_of[(size_t)a.dep_base[r] + row[i]] : 0u;
         const uint32_t ext_pad = align16(4u * n_ext) / 4u;
         for (uint32_t i = n_ext + tid; i < ext_pad; i += blockDim.x) ext[i] = 0u;   // entries proper: tile blocks
         const uint32_t cell_pad = align16(4u * n_cells) / 4u;
@@ -348,6 +452,7 @@ p_fill_kernel(PFillArgs a) {
         const uint32_t k = a.k32[s];
         const uint32_t c = k / a.n_dl, dl = k - c * a.n_dl;
         const uint32_t pc = a.pg.patch_of[c];
+        const uint8_t *const ph = a.phase ? a.phase + (size_t)dl * a.g.n_cells : nullptr;
         lcell[tid] = (uint16_t)(a.pg.lidx[c] | ((uint32_t)a.group_rank[dl] << 10));
         const uint32_t e0 = (uint32_t)(a.upoff[s] - e_base);
         uint32_t e = e0, n_per = 0;
@@ -363,7 +468,7 @@ p_fill_kernel(PFillArgs a) {
                 const double tt = a.ttot_slot[src];
                 const double share = tt > 0.0 ? (a.g.face_rev[f] * (-dd)) / tt : 0.0;
                 uint32_t vi;
-                if (pass == 0 && a.pg.patch_of[nb] == pc) {
+                if (pass == 0 && a.pg.patch_of[nb] == pc && (!ph || ph[nb] == ph[c])) {
                     vi = src - mt0;   // a slot of this macro-tile in an earlier sub-level
                     if (src < mt0 || src >= slot0) atomicExch(a.counters + 3, 1u);
                 } else {
@@ -459,6 +564,7 @@ struct PatchArgs {
     double threshold;
     uint32_t stages, stage_bytes, vmax, pc_max, smax;
     uint32_t n_cells, epoch, poll_ns;
+    uint32_t accumulate;      // phases: a (group, cell) rate row is split over several macro-tiles -> add instead of store
     unsigned long long *prof; // optional per-block cycle counters, 10 per block (SSW_STREAM_PROFILE)
 };
 
@@ -536,6 +642,8 @@ patch_sweep_kernel(PatchArgs a) {
                     s_cellid[i] = c;
                     s_rec[i] = __ldg(a.cellrec + c);
                 }
+                if (a.accumulate)   // ragged macro-tile: not every (cell, direction) of the patch has a task here
+                    for (uint32_t i = tid - 32u; i < n_cells * kdg; i += THREADS - 32u) s_inc[i] = 0.0;
             }
             __syncthreads();
             double *const vx = val + n_slots;
@@ -614,13 +722,27 @@ patch_sweep_kernel(PatchArgs a) {
                 //      done flag goes out first (the release is cumulative over the block's stores; downwind macro-tiles
                 //      are waiting for it).  Then sum_d incoming of the group's directions per cell, in direction order
                 //      (src/sweep/mod.rs:554-558): plain stores, every (group, cell) is written exactly once per sweep
-                if (tid == 0) st_release_gpu(a.mt_flag + rank, a.epoch);
                 double *const acc = a.acc_cell + (size_t)group * a.n_cells;
-                for (uint32_t i = tid; i < n_cells; i += THREADS) {
-                    const double *const row = s_inc + i * kdg;
-                    double sum = 0.0;
-                    for (uint32_t j = 0; j < kdg; ++j) sum += row[j];
-                    __stcg(acc + s_cellid[i], sum);
+                if (!a.accumulate) {
+                    if (tid == 0) st_release_gpu(a.mt_flag + rank, a.epoch);
+                    for (uint32_t i = tid; i < n_cells; i += THREADS) {
+                        const double *const row = s_inc + i * kdg;
+                        double sum = 0.0;
+                        for (uint32_t j = 0; j < kdg; ++j) sum += row[j];
+                        __stcg(acc + s_cellid[i], sum);
+                    }
+                } else {
+                    // phases of one (patch, group) are chained through their done flags, so the read-modify-write of
+                    // the row is ordered; it has to be complete before the flag goes out
+                    for (uint32_t i = tid; i < n_cells; i += THREADS) {
+                        const double *const row = s_inc + i * kdg;
+                        double sum = 0.0;
+                        for (uint32_t j = 0; j < kdg; ++j) sum += row[j];
+                        double *const dst = acc + s_cellid[i];
+                        __stcg(dst, __ldcg(dst) + sum);
+                    }
+                    __syncthreads();
+                    if (tid == 0) st_release_gpu(a.mt_flag + rank, a.epoch);
                 }
                 // no barrier: the next head fills the other s_cellid buffer, and two barriers separate it from the
                 // next write to s_inc
@@ -746,7 +868,7 @@ inline bool level_macro_tiles(const unsigned int *dep, uint32_t G, uint32_t P, s
 inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGrid &pg, const double *dirs_local,
                                    const uint32_t *tasks, const uint32_t *level_off_dev, uint64_t n_tasks,
                                    uint32_t n_levels, int n_local_dirs, const uint32_t *pcells, uint32_t n_periodic,
-                                   const double *q_nat,
+                                   const double *q_nat, const std::vector<uint32_t> *level_off_host,
                                    int num_sms, cudaStream_t stream, uint64_t *launch_counter) {
     C.release();
     if (n_tasks >= 0x7fffff00ull) throw PatchUnsupported("more than 2^31 tasks per rank");
@@ -796,24 +918,143 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
         }
         std::vector<uint32_t> mt_level, ndep;
         uint32_t max_level = 0;
-        if (!level_macro_tiles(dep_h.data(), G, P, mt_level, ndep, max_level))
-            throw PatchUnsupported("patches depend on each other cyclically for a direction group");
-        std::vector<uint32_t> mt_list;   // grp * P + p of every non-empty macro-tile, in rank order
-        mt_list.reserve((size_t)G * P);
-        for (uint32_t grp = 0; grp < G; ++grp)
-            for (uint32_t p = 0; p < P; ++p)
-                if (patch_size[p]) mt_list.push_back(grp * P + p);
-        std::stable_sort(mt_list.begin(), mt_list.end(), [&](uint32_t x, uint32_t y) {
-            if (mt_level[x] != mt_level[y]) return mt_level[x] < mt_level[y];
-            return (x % P) != (y % P) ? (x % P) < (y % P) : x < y;   // same level: neighbouring patches of all groups together
-        });
-        const uint32_t n_mt = (uint32_t)mt_list.size();
-        std::vector<uint32_t> rank_of((size_t)G * P, 0xffffffffu), mt_group(n_mt), mt_patch(n_mt), mt_ndep(n_mt);
-        for (uint32_t r = 0; r < n_mt; ++r) {
-            rank_of[mt_list[r]] = r;
-            mt_group[r] = mt_list[r] / P;
-            mt_patch[r] = mt_list[r] % P;
-            mt_ndep[r] = ndep[mt_list[r]];
+        // per macro-tile (rank order): group, patch, number of upwind macro-tiles, row in dep_tab, offset of its dep_tab
+        // entries in rank_of
+        std::vector<uint32_t> rank_of, mt_group, mt_patch, mt_ndep, mt_row, dep_base;
+        uint32_t n_mt = 0, n_phase = 1, kd_max = 1;
+        for (uint32_t k : group_kd) kd_max = std::max(kd_max, k);
+        DTmp<uint8_t> phase_dev;          // phases only: phase of every task
+        DTmp<uint32_t> mtid_dev;          // phases only: (group, patch, phase) -> dense macro-tile id
+        DTmp<unsigned int> minlev2;       // phases only: smallest level per (macro-tile, direction of the group)
+        const bool phases = !level_macro_tiles(dep_h.data(), G, P, mt_level, ndep, max_level);
+        if (!phases) {
+            std::vector<uint32_t> mt_list;   // grp * P + p of every non-empty macro-tile, in rank order
+            mt_list.reserve((size_t)G * P);
+            for (uint32_t grp = 0; grp < G; ++grp)
+                for (uint32_t p = 0; p < P; ++p)
+                    if (patch_size[p]) mt_list.push_back(grp * P + p);
+            std::stable_sort(mt_list.begin(), mt_list.end(), [&](uint32_t x, uint32_t y) {
+                if (mt_level[x] != mt_level[y]) return mt_level[x] < mt_level[y];
+                return (x % P) != (y % P) ? (x % P) < (y % P) : x < y;   // same level: neighbouring patches of all groups together
+            });
+            n_mt = (uint32_t)mt_list.size();
+            rank_of.assign((size_t)G * P, 0xffffffffu);
+            mt_group.resize(n_mt); mt_patch.resize(n_mt); mt_ndep.resize(n_mt); mt_row.resize(n_mt); dep_base.resize(n_mt);
+            for (uint32_t r = 0; r < n_mt; ++r) {
+                rank_of[mt_list[r]] = r;
+                mt_group[r] = mt_list[r] / P;
+                mt_patch[r] = mt_list[r] % P;
+                mt_ndep[r] = ndep[mt_list[r]];
+                mt_row[r] = mt_list[r];
+                dep_base[r] = mt_group[r] * P;
+            }
+        } else {
+            // The patch graph of some group is cyclic (a jagged Voronoi patch boundary carries flux both ways for
+            // directions nearly parallel to it).  Split the macro-tiles into phases (see p_phase_kernel).
+            if (!env_u32("SSW_PATCH_PHASES", 1))
+                throw PatchUnsupported("patches depend on each other cyclically for a direction group");
+            if (!level_off_host || level_off_host->size() != (size_t)n_levels + 1)
+                throw PatchUnsupported("cyclic patch graph and no host copy of the level offsets");
+            // a. total order pi of the patches per group: along the octant of the group's directions
+            std::vector<uint32_t> pi((size_t)G * P);
+            {
+                std::vector<int> sgn((size_t)G * 3, 1);
+                for (uint32_t dl = 0; dl < n_dl; ++dl)
+                    for (int k = 0; k < 3; ++k)
+                        if (dirs_local[3 * dl + k] < 0.0) sgn[(size_t)group_of[dl] * 3 + k] = -1;
+                std::vector<uint64_t> key(P);
+                std::vector<uint32_t> order(P);
+                for (uint32_t grp = 0; grp < G; ++grp) {
+                    for (uint32_t p = 0; p < P; ++p) {
+                        uint32_t b[3] = {p / (pg.dims[1] * pg.dims[2]), (p / pg.dims[2]) % pg.dims[1], p % pg.dims[2]};
+                        uint64_t o[3];
+                        for (int k = 0; k < 3; ++k) o[k] = sgn[(size_t)grp * 3 + k] > 0 ? b[k] : pg.dims[k] - 1 - b[k];
+                        key[p] = ((o[0] + o[1] + o[2]) << 40) | (o[0] << 26) | (o[1] << 13) | o[2];
+                        order[p] = p;
+                    }
+                    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return key[x] < key[y]; });
+                    for (uint32_t i = 0; i < P; ++i) pi[(size_t)grp * P + order[i]] = i;
+                }
+            }
+            DTmp<uint32_t> pi_dev; pi_dev.upload(pi, stream, "pi");
+            // b. phases, level by level
+            phase_dev.alloc(n, "phase");
+            cuda_ok(cudaMemsetAsync(phase_dev.p, 0, n, stream), "memset phase");
+            for (uint32_t l = 0; l < n_levels; ++l) {
+                const uint32_t s0 = (*level_off_host)[l], s1 = (*level_off_host)[l + 1];
+                if (s1 > s0)
+                    p_phase_kernel<<<(s1 - s0 + 255) / 256, 256, 0, stream>>>(g, tasks, s0, s1, pg.patch_of, group_dev.p, P, pi_dev.p,
+                                                                            phase_dev.p, counters.p);
+            }
+            launches += n_levels;
+            cuda_ok(cudaMemcpyAsync(cnt_h, counters.p, sizeof cnt_h, cudaMemcpyDeviceToHost, stream), "copy counters");
+            cuda_ok(cudaStreamSynchronize(stream), "phase sync");
+            if (cnt_h[7]) throw PatchUnsupported("more than 255 phases");
+            n_phase = cnt_h[6] + 1;
+            const uint64_t n_keys64 = (uint64_t)G * P * n_phase;
+            if (n_keys64 > (64ull << 20)) throw PatchUnsupported("too many (group, patch, phase) triples");
+            const uint32_t n_keys = (uint32_t)n_keys64;
+            // c. dense macro-tile ids
+            DTmp<uint32_t> present, scan, mt_key_dev;
+            present.alloc((size_t)n_keys + 1, "present");
+            scan.alloc((size_t)n_keys + 1, "scan");
+            mtid_dev.alloc(n_keys, "mtid_of");
+            cuda_ok(cudaMemsetAsync(present.p, 0, sizeof(uint32_t) * ((size_t)n_keys + 1), stream), "memset present");
+            p_present_kernel<<<blocks_n, 256, 0, stream>>>(N, n_dl, pg.patch_of, group_dev.p, P, n_phase, phase_dev.p, present.p);
+            {
+                size_t bytes = 0;
+                DTmp<unsigned char> temp;
+                cuda_ok(cub::DeviceScan::ExclusiveSum(nullptr, bytes, present.p, scan.p, (int)n_keys + 1, stream), "scan size");
+                temp.alloc(bytes, "scan temp");
+                cuda_ok(cub::DeviceScan::ExclusiveSum(temp.p, bytes, present.p, scan.p, (int)n_keys + 1, stream), "scan");
+                cuda_ok(cudaMemcpyAsync(&n_mt, scan.p + n_keys, sizeof n_mt, cudaMemcpyDeviceToHost, stream), "copy n_mt");
+                cuda_ok(cudaStreamSynchronize(stream), "scan sync");
+            }
+            if (n_mt == 0 || n_mt > kMaxRank) throw PatchUnsupported("more than 2^20 macro-tiles");
+            mt_key_dev.alloc(n_mt, "mt_key");
+            p_mtid_kernel<<<(n_keys + 255) / 256, 256, 0, stream>>>(present.p, scan.p, n_keys, mtid_dev.p, mt_key_dev.p);
+            std::vector<uint32_t> mt_key(n_mt);
+            cuda_ok(cudaMemcpyAsync(mt_key.data(), mt_key_dev.p, sizeof(uint32_t) * (size_t)n_mt, cudaMemcpyDeviceToHost, stream), "copy mt_key");
+            // d. quotient graph over the macro-tiles, smallest level per (macro-tile, direction of the group)
+            dep_tab.alloc((size_t)n_mt * kMaxPatchDeps, "dep_tab2");
+            minlev2.alloc((size_t)n_mt * kd_max, "minlev2");
+            cuda_ok(cudaMemsetAsync(dep_tab.p, 0xff, sizeof(unsigned int) * (size_t)n_mt * kMaxPatchDeps, stream), "memset");
+            cuda_ok(cudaMemsetAsync(minlev2.p, 0xff, sizeof(unsigned int) * (size_t)n_mt * kd_max, stream), "memset");
+            p_edges2_kernel<<<blocks_n, 256, 0, stream>>>(g, n_dl, pg.patch_of, group_dev.p, group_rank_dev.p, P, n_phase, kd_max,
+                                                       phase_dev.p, mtid_dev.p, tlevel.p, dep_tab.p, minlev2.p, counters.p + 4);
+            dep_h.assign((size_t)n_mt * kMaxPatchDeps, kEmptyDep);
+            cuda_ok(cudaMemcpyAsync(dep_h.data(), dep_tab.p, sizeof(unsigned int) * dep_h.size(), cudaMemcpyDeviceToHost, stream), "copy dep_tab2");
+            cuda_ok(cudaMemcpyAsync(cnt_h, counters.p, sizeof cnt_h, cudaMemcpyDeviceToHost, stream), "copy counters");
+            cuda_ok(cudaStreamSynchronize(stream), "quotient graph 2 sync");
+            launches += 6;
+            if (cnt_h[4]) throw PatchUnsupported("a macro-tile has more than 32 upwind macro-tiles");
+            // chain the phases of one (group, patch): their rate rows are accumulated in phase order.  Ids grow with the
+            // key (group, patch, phase), so the previous phase of the same (group, patch) is the previous id.
+            for (uint32_t id = 1; id < n_mt; ++id) {
+                if (mt_key[id] / n_phase != mt_key[id - 1] / n_phase) continue;
+                unsigned int *row = dep_h.data() + (size_t)id * kMaxPatchDeps;
+                uint32_t k = 0;
+                while (k < kMaxPatchDeps && row[k] != kEmptyDep && row[k] != id - 1) ++k;
+                if (k == kMaxPatchDeps) throw PatchUnsupported("a macro-tile has more than 32 upwind macro-tiles");
+                row[k] = id - 1;
+            }
+            cuda_ok(cudaMemcpyAsync(dep_tab.p, dep_h.data(), sizeof(unsigned int) * dep_h.size(), cudaMemcpyHostToDevice, stream), "copy dep_tab2");
+            // e. levels and global order of the macro-tiles
+            if (!level_macro_tiles(dep_h.data(), 1, n_mt, mt_level, ndep, max_level))
+                throw std::runtime_error("compile_patch_schedule: macro-tile graph with phases is cyclic");
+            std::vector<uint32_t> mt_list(n_mt);
+            std::iota(mt_list.begin(), mt_list.end(), 0u);
+            std::stable_sort(mt_list.begin(), mt_list.end(), [&](uint32_t x, uint32_t y) { return mt_level[x] < mt_level[y]; });
+            rank_of.assign(n_mt, 0xffffffffu);
+            mt_group.resize(n_mt); mt_patch.resize(n_mt); mt_ndep.resize(n_mt); mt_row.resize(n_mt); dep_base.assign(n_mt, 0u);
+            for (uint32_t r = 0; r < n_mt; ++r) {
+                const uint32_t id = mt_list[r], gp = mt_key[id] / n_phase;
+                rank_of[id] = r;
+                mt_group[r] = gp / P;
+                mt_patch[r] = gp % P;
+                mt_ndep[r] = ndep[id];
+                mt_row[r] = id;
+            }
         }
         DTmp<uint32_t> rank_dev; rank_dev.upload(rank_of, stream, "rank_of");
 
@@ -821,8 +1062,13 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
         DTmp<unsigned long long> keys_in, keys;
         keys_in.alloc(n, "keys_in");
         keys.alloc(n, "keys");
-        p_key_kernel<<<blocks_n, 256, 0, stream>>>(N, n_dl, pg.patch_of, group_dev.p, P, rank_dev.p, tlevel.p, minlev.p,
-                                                  keys_in.p, counters.p + 5);
+        if (!phases)
+            p_key_kernel<<<blocks_n, 256, 0, stream>>>(N, n_dl, pg.patch_of, group_dev.p, P, rank_dev.p, tlevel.p, minlev.p,
+                                                      keys_in.p, counters.p + 5);
+        else
+            p_key2_kernel<<<blocks_n, 256, 0, stream>>>(N, n_dl, pg.patch_of, group_dev.p, group_rank_dev.p, P, n_phase, kd_max,
+                                                       phase_dev.p, mtid_dev.p, rank_dev.p, tlevel.p, minlev2.p, keys_in.p,
+                                                       counters.p + 5);
         ++launches;
         {
             size_t bytes = 0;
@@ -885,7 +1131,8 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
         cuda_ok(cudaMemsetAsync(cnt_e.p + n, 0, sizeof(uint32_t), stream), "memset");
         cuda_ok(cudaMemsetAsync(cnt_x.p + n, 0, sizeof(uint32_t), stream), "memset");
         s_slot_scatter_kernel<<<blocks_n, 256, 0, stream>>>(k32.p, n, N, n_dl, C.slot_of);
-        p_count_kernel<<<blocks_n, 256, 0, stream>>>(g, k32.p, n, n_dl, pg.patch_of, cnt_e.p, cnt_x.p, C.ttot_slot, counters.p);
+        p_count_kernel<<<blocks_n, 256, 0, stream>>>(g, k32.p, n, n_dl, pg.patch_of, phases ? phase_dev.p : nullptr, cnt_e.p, cnt_x.p,
+                                                    C.ttot_slot, counters.p);
         {
             cub::TransformInputIterator<unsigned long long, CastU64, const uint32_t *> in_e(cnt_e.p, CastU64()), in_x(cnt_x.p, CastU64());
             size_t bytes = 0;
@@ -961,8 +1208,9 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
             const uint64_t ns = mt_slot0_h[r + 1] - mt_slot0_h[r];
             if (ns + n_ext > 65535ull) throw PatchUnsupported("a macro-tile holds more than 65535 values (smaller patches or direction groups needed)");
             vmax = std::max<uint32_t>(vmax, (uint32_t)(ns + n_ext));
-            smax = std::max<uint32_t>(smax, (uint32_t)ns);
-            if (ns != (uint64_t)patch_size[mt_patch[r]] * group_kd[mt_group[r]])
+            const uint64_t full = (uint64_t)patch_size[mt_patch[r]] * group_kd[mt_group[r]];   // rows of the rate reduction
+            smax = std::max<uint32_t>(smax, (uint32_t)full);
+            if (phases ? ns > full : ns != full)
                 throw std::runtime_error("compile_patch_schedule: macro-tile is not (patch cells) x (group directions)");
             pc_max = std::max(pc_max, patch_size[mt_patch[r]]);
             head_bytes[r] = head_layout(mt_ndep[r], (uint32_t)n_ext, patch_size[mt_patch[r]]).bytes;
@@ -1035,7 +1283,9 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
         cuda_ok(cudaMemcpyAsync(C.ptab, ptab.data(), sizeof(PDesc) * (size_t)n_packets, cudaMemcpyHostToDevice, stream), "copy ptab");
         cuda_ok(cudaMemcpyAsync(C.tab_off, tab_off.data(), sizeof(uint32_t) * ((size_t)nb + 1), cudaMemcpyHostToDevice, stream), "copy");
         cuda_ok(cudaMemcpyAsync(C.stream_off, stream_off.data(), sizeof(uint64_t) * ((size_t)nb + 1), cudaMemcpyHostToDevice, stream), "copy");
-        DTmp<uint32_t> ptab_block_dev, tile_rank_dev, mt_group_dev, mt_patch_dev, mt_ndep_dev;
+        DTmp<uint32_t> ptab_block_dev, tile_rank_dev, mt_group_dev, mt_patch_dev, mt_ndep_dev, mt_row_dev, dep_base_dev;
+        mt_row_dev.upload(mt_row, stream, "mt_row");
+        dep_base_dev.upload(dep_base, stream, "dep_base");
         DTmp<uint64_t> head_off_dev;
         ptab_block_dev.upload(ptab_block, stream, "ptab_block");
         tile_rank_dev.upload(tile_rank, stream, "tile_rank");
@@ -1053,6 +1303,7 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
         fa.mt_group = mt_group_dev.p; fa.mt_patch = mt_patch_dev.p; fa.mt_ndep = mt_ndep_dev.p; fa.head_off = head_off_dev.p;
         fa.group_rank = group_rank_dev.p; fa.group_kd = group_kd_dev.p;
         fa.dep_tab = dep_tab.p; fa.rank_of = rank_dev.p; fa.lag_src = C.lag_src; fa.counters = counters.p;
+        fa.mt_row = mt_row_dev.p; fa.dep_base = dep_base_dev.p; fa.phase = phases ? phase_dev.p : nullptr;
         if (n_packets) p_fill_kernel<<<n_packets, 256, 0, stream>>>(fa);
         s_convert_state_kernel<<<blocks_n, 256, 0, stream>>>(k32.p, n, N, n_dl, q_nat, C.ttot_slot, C.out_slot);
         cuda_ok(cudaGetLastError(), "patch compile kernels");
@@ -1106,6 +1357,8 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
         C.n_groups_per = 1;
         C.epoch = 0;
         C.patch_mode = true;
+        C.accumulate = phases;
+        C.n_phases = n_phase;
     } catch (...) {
         C.release();
         if (launch_counter) *launch_counter += launches;
@@ -1141,6 +1394,8 @@ inline void run_patch(Compiled &C, const double2 *cellrec, double threshold, cud
     a.smax = C.smax;
     a.n_cells = C.n_cells;
     a.epoch = ++C.epoch;
+    a.accumulate = C.accumulate ? 1u : 0u;
+    if (C.accumulate) cuda_ok(cudaMemsetAsync(C.acc_cell, 0, sizeof(double) * (size_t)C.n_groups * C.n_cells, stream), "memset acc_cell");
     a.poll_ns = env_u32("SSW_STREAM_POLL_NS", 20);
     a.prof = nullptr;
     unsigned long long *prof_dev = nullptr;

@@ -136,6 +136,8 @@ struct Compiled {
     double *acc_per = nullptr;      // G x n_periodic: sum_d periodic_source (patch mode: one row)
     // patch-ordered form (patch.cuh): macro-tiles (patch, direction group) with point-to-point done flags
     bool patch_mode = false;
+    bool accumulate = false;        // patch mode with phases (cyclic patch graph): rate rows are accumulated
+    uint32_t n_phases = 1;
     uint32_t n_groups_per = 1;      // rows of acc_per
     uint32_t n_mt = 0, vmax = 0, pc_max = 0, smax = 0, epoch = 0;
     uint32_t kd = 0, n_patches = 0, patch_levels = 0;
@@ -156,6 +158,8 @@ struct Compiled {
         mt_flag = nullptr;
         ptab = nullptr;
         patch_mode = false;
+        accumulate = false;
+        n_phases = 1;
         slot_of = lag_src = tab_off = lvl_target = lvl_dep = nullptr;
         out_slot = ttot_slot = acc_cell = acc_per = nullptr;
         stream = nullptr;

@@ -135,7 +135,7 @@ struct Sweep {
     // spatial patches (ssw_set_cell_positions): cell -> patch map of the patch-ordered all-cells sweep (patch.cuh)
     DevBuf<uint32_t> patch_of, patch_off, patch_cells;
     DevBuf<uint16_t> patch_lidx;
-    uint32_t n_patches = 0, patch_max_cells = 0;
+    uint32_t n_patches = 0, patch_max_cells = 0, patch_dims[3] = {1, 1, 1};
     bool have_patches = false;
     std::string patch_note;   // why the patch-ordered form is not in use (empty: it is, or was never tried)
     // per (dir, cell)
@@ -297,6 +297,7 @@ struct Sweep {
         PatchGrid pg;
         pg.patch_of = patch_of.p; pg.lidx = patch_lidx.p; pg.patch_off = patch_off.p; pg.patch_cells = patch_cells.p;
         pg.n_patches = n_patches; pg.max_cells = patch_max_cells;
+        for (int k = 0; k < 3; ++k) pg.dims[k] = patch_dims[k];
         return pg;
     }
     void refresh_histogram();
@@ -476,7 +477,7 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
 // for the CPU tests).  Returns the number of patches, 0 if no lattice qualifies (`why` says why).
 static uint32_t build_patch_lattice(const double *xyz, uint32_t N, double target, std::vector<uint32_t> &pof,
                                     std::vector<uint32_t> &poff, std::vector<uint32_t> &pcl, std::vector<uint16_t> &lidx,
-                                    uint32_t &max_cells, std::string &why) {
+                                    uint32_t &max_cells, std::string &why, uint32_t lattice[3]) {
     double lo[3], hi[3];
     for (int k = 0; k < 3; ++k) { lo[k] = std::numeric_limits<double>::infinity(); hi[k] = -lo[k]; }
     for (uint32_t c = 0; c < N; ++c)
@@ -535,6 +536,7 @@ static uint32_t build_patch_lattice(const double *xyz, uint32_t N, double target
             lidx[c] = (uint16_t)(pos - poff[pof[c]]);
         }
         max_cells = mx;
+        for (int k = 0; k < 3; ++k) lattice[k] = nbx[k];
         return Pn;
     }
     why = "no patch lattice with <= 1024 cells per patch";
@@ -553,7 +555,7 @@ void Sweep::set_positions(const double *xyz) {
     std::vector<uint32_t> pof, poff, pcl;
     std::vector<uint16_t> lidx;
     uint32_t mx = 0;
-    const uint32_t Pn = build_patch_lattice(xyz, N, target, pof, poff, pcl, lidx, mx, patch_note);
+    const uint32_t Pn = build_patch_lattice(xyz, N, target, pof, poff, pcl, lidx, mx, patch_note, patch_dims);
     if (!Pn) return;
     CUDA_CHECK(cudaSetDevice(device));
     patch_of.alloc(N); patch_of.upload(pof.data(), N, stream);
@@ -780,11 +782,12 @@ void Sweep::single_sweep(int cur) {
                     try {
                         compile_patch_schedule(S.compiled, grid_view(), patch_view(), dirs_all.data() + 3 * (size_t)d0,
                                                S.tasks.p, S.level_off.p, S.n_tasks, S.n_levels, Dl, pcells.p, n_periodic, q.p,
-                                               num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
+                                               &S.level_off_host, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
                         patched = true;
                         patch_note.clear();
                         stat[SSW_STAT_PATCH_MACRO_TILES] = S.compiled.n_mt;
                         stat[SSW_STAT_PATCH_LEVELS] = S.compiled.patch_levels;
+                        stat[SSW_STAT_PATCH_PHASES] = S.compiled.n_phases;
                     } catch (const PatchUnsupported &e) {
                         patch_note = e.what();   // keep the level-barrier stream
                     }
@@ -1322,7 +1325,8 @@ int32_t ssw_patch_lattice(const double *xyz, uint64_t n_cells, int32_t target_ce
         std::vector<uint16_t> lidx;
         uint32_t mx = 0;
         std::string why;
-        const uint32_t Pn = ssw::build_patch_lattice(xyz, (uint32_t)n_cells, (double)target_cells, pof, poff, pcl, lidx, mx, why);
+        uint32_t dims[3];
+        const uint32_t Pn = ssw::build_patch_lattice(xyz, (uint32_t)n_cells, (double)target_cells, pof, poff, pcl, lidx, mx, why, dims);
         if (!Pn) { ssw::g_last_error = why; return 0; }
         std::copy(pof.begin(), pof.end(), patch_of);
         return (int32_t)Pn;

@@ -29,6 +29,7 @@ def run(params, g, f, flags, steps):
     out["patch_levels"] = s.stat("patch_levels")
     out["wavefront_levels"] = s.stat("wavefront_levels")
     out["note"] = s.patch_note()
+    out["phases"] = s.stat("patch_phases")
     s.close()
     return out
 
@@ -70,3 +71,22 @@ def test_patch_default_against_oracle_with_timestep_levels(cuda_lib, monkeypatch
     assert_close(got.read("photon_rate"), b, 1e-6, floor=1e-7 * np.nanmax(np.abs(b)), what="photon_rate")
     assert np.array_equal(got.levels(), ref.levels())
     assert got.stat("tasks_solved") == ref.stat("tasks_solved")
+
+
+@pytest.mark.parametrize("kind,n,periodic,n_dirs,patch_cells", [
+    ("voronoi", 9, True, 84, 27), ("voronoi", 9, False, 21, 64), ("jittered", 8, True, 16, 27), ("voronoi", 10, True, 21, 125),
+])
+def test_patch_form_with_phases_matches_stream_form_on_voronoi_grids(cuda_lib, monkeypatch, kind, n, periodic, n_dirs, patch_cells):
+    """Voronoi grids have cyclic patch graphs; the macro-tiles are then split into phases (patch.cuh, p_phase_kernel).
+    Same per-task arithmetic as the stream form: outgoing rates bit-identical after a sweep from the same state."""
+    monkeypatch.setenv("SSW_PATCH_CELLS", str(patch_cells))
+    monkeypatch.setenv("SSW_PATCH_PHASES", "1")
+    params, g, f = make_problem(kind, n, periodic, n_dirs=n_dirs, n_levels=1)
+    a = run(params, g, f, 0, 2)
+    b = run(params, g, f, capi.FLAG_NO_PATCH_PATH, 2)
+    assert a["macro_tiles"] > 0 and a["note"] == "", a["note"]
+    assert b["macro_tiles"] == 0
+    assert np.array_equal(a["outgoing"], b["outgoing"])
+    assert np.array_equal(a["levels"], b["levels"])
+    for k in FIELDS + ("incoming", "periodic"):
+        assert_close(a[k], b[k], 1e-12, floor=1e-9 * max(np.nanmax(np.abs(b[k])), 1e-300), what=k)
