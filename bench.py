@@ -362,6 +362,7 @@ def run_b200(args) -> None:
                               "sweep_ms": tim["sweep_ms"] / args.steps, "chemistry_ms": tim["chemistry_ms"] / args.steps,
                               "all_cells_form": "patch dataflow" if sweep.stat("patch_macro_tiles") else "level-barrier stream (" + (sweep.patch_note() or "patch form off") + ")",
                               "macro_tiles": sweep.stat("patch_macro_tiles"), "patch_levels": sweep.stat("patch_levels"),
+                              "patch_phases": sweep.stat("patch_phases"),
                               "mean_xhii": float(sweep.read("ionized_hydrogen_fraction").mean()),
                               "env": {k: v for k, v in os.environ.items() if k.startswith("SSW_")},
                               "note": "profiling run (--no-e2e): not a bench line"}), flush=True)

@@ -265,7 +265,7 @@ int32_t ssw_patch_lattice(const double *xyz /* N x 3 */, uint64_t n_cells, int32
                           uint32_t *patch_of /* N */);
 int32_t ssw_direction_groups(const double *dirs_xyz /* D x 3 */, int32_t n_dirs, int32_t max_per_group,
                              int32_t *group_of /* D */);
-/* ssw_patch_levels: level of every macro-tile from the quotient graph; upwind[(g * P + p) * 32 ..] lists the upwind
+/* ssw_patch_levels: level of every macro-tile from the quotient graph; upwind[(g * P + p) * 64 ..] lists the upwind
  * patches of patch p for group g, terminated by 0xffffffff.  Returns the number of levels, SSW_E_DEADLOCK if a
  * group's graph has a cycle (the grid then keeps the level-barrier stream). */
 int32_t ssw_patch_levels(const uint32_t *upwind, int32_t n_groups, int32_t n_patches, uint32_t *level_out /* G x P */);

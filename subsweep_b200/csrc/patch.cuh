@@ -16,7 +16,7 @@
 //     are gathered from global memory once, when the macro-tile starts;
 //   * macro-tiles depend on each other through the quotient graph patch -> patch of their direction
 //     group.  Every macro-tile owns a done flag (the epoch of the sweep that completed it); a
-//     macro-tile acquire-polls the flags of its (<= 32) upwind macro-tiles and releases its own.
+//     macro-tile acquire-polls the flags of its (<= 64) upwind macro-tiles and releases its own.
 //     No device-wide barrier at all: a 128^3 grid has 46 dependent macro-tile levels instead of 383
 //     wavefront levels.  Blocks consume macro-tiles in a global topological order (rank), dealt
 //     round-robin, all blocks co-resident (cooperative launch): the lowest unfinished rank is always
@@ -55,7 +55,7 @@ struct PatchUnsupported : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
-constexpr uint32_t kMaxPatchDeps = 32;
+constexpr uint32_t kMaxPatchDeps = 64;
 constexpr uint32_t kMaxPatchCells = 1024;
 constexpr uint32_t kEmptyDep = 0xffffffffu;
 constexpr int kRankShift = 44;       // sort key = rank << 44 | sub-level << 32 | (cell * Dl + dl)
@@ -156,7 +156,7 @@ p_level_kernel(const uint32_t *__restrict__ tasks, uint32_t n, const uint32_t *_
     atomicMin(minlev + (size_t)patch_of[c] * n_dl + dl, lo);
 }
 
-// quotient graph: dep_tab[(group * P + patch) * 32 ..] = set of patches with a Local face into `patch`
+// quotient graph: dep_tab[(group * P + patch) * 64 ..] = set of patches with a Local face into `patch`
 // that is upwind for a direction of `group` (init_counts, src/sweep/mod.rs:346-386, lifted to patches)
 __global__ void __launch_bounds__(256)
 p_edges_kernel(GridView g, uint32_t n_dl, const uint32_t *__restrict__ patch_of, const uint16_t *__restrict__ group_of,
@@ -232,7 +232,7 @@ p_mtid_kernel(const uint32_t *__restrict__ present, const uint32_t *__restrict__
     else mtid_of[k] = 0xffffffffu;
 }
 
-// quotient graph over macro-tiles with phases: dep_tab[id * 32 ..] = upwind macro-tiles; smallest wavefront level of
+// quotient graph over macro-tiles with phases: dep_tab[id * 64 ..] = upwind macro-tiles; smallest wavefront level of
 // every (macro-tile, direction of the group)
 __global__ void __launch_bounds__(256)
 p_edges2_kernel(GridView g, uint32_t n_dl, const uint32_t *__restrict__ patch_of, const uint16_t *__restrict__ group_of,
@@ -630,9 +630,11 @@ patch_sweep_kernel(PatchArgs a) {
                 // warp 0 only polls: the flag round trips start at once and run beside the staging of the other warps
                 if (tid < n_dep) {
                     if (PROFILE && tid == 0) tp = clock64();
-                    const unsigned int *flag = a.mt_flag + dep[tid];
-                    // relaxed polls (no L1 invalidation per round trip), one acquire fence once the flag is there
-                    while (ld_relaxed_gpu(flag) != a.epoch) __nanosleep(a.poll_ns);
+                    // relaxed polls (no L1 invalidation per round trip), one acquire fence once the flags are there
+                    for (uint32_t i = tid; i < n_dep; i += 32u) {
+                        const unsigned int *flag = a.mt_flag + dep[i];
+                        while (ld_relaxed_gpu(flag) != a.epoch) __nanosleep(a.poll_ns);
+                    }
                     fence_acq_rel_gpu();
                     if (PROFILE && tid == 0) t_poll += clock64() - tp;
                 }
@@ -818,7 +820,7 @@ inline uint32_t make_direction_groups(const double *dirs_local, uint32_t n_dl, u
     return G;
 }
 
-// Levels of the macro-tiles: Kahn's algorithm over the quotient graph of every group.  dep[(grp * P + p) * 32 ..] lists
+// Levels of the macro-tiles: Kahn's algorithm over the quotient graph of every group.  dep[(grp * P + p) * 64 ..] lists
 // the upwind patches of patch p (kEmptyDep-terminated).  level = 1 + max level of the upwind macro-tiles (0: none).
 // Returns false if some group's graph has a cycle.  Pure host code (also behind ssw_patch_levels for the CPU tests).
 inline bool level_macro_tiles(const unsigned int *dep, uint32_t G, uint32_t P, std::vector<uint32_t> &mt_level,
@@ -907,7 +909,7 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
         cuda_ok(cudaMemcpyAsync(dep_h.data(), dep_tab.p, sizeof(unsigned int) * dep_h.size(), cudaMemcpyDeviceToHost, stream), "copy dep_tab");
         cuda_ok(cudaMemcpyAsync(cnt_h, counters.p, sizeof cnt_h, cudaMemcpyDeviceToHost, stream), "copy counters");
         cuda_ok(cudaStreamSynchronize(stream), "quotient graph sync");
-        if (cnt_h[4]) throw PatchUnsupported("a patch has more than 32 upwind patches");
+        if (cnt_h[4]) throw PatchUnsupported("a patch has more than 64 upwind patches");
 
         // 2. macro-tile levels (Kahn over the quotient graph of every group) -> global order
         std::vector<uint32_t> patch_size(P);
@@ -1027,7 +1029,7 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
             cuda_ok(cudaMemcpyAsync(cnt_h, counters.p, sizeof cnt_h, cudaMemcpyDeviceToHost, stream), "copy counters");
             cuda_ok(cudaStreamSynchronize(stream), "quotient graph 2 sync");
             launches += 6;
-            if (cnt_h[4]) throw PatchUnsupported("a macro-tile has more than 32 upwind macro-tiles");
+            if (cnt_h[4]) throw PatchUnsupported("a macro-tile has more than 64 upwind macro-tiles");
             // chain the phases of one (group, patch): their rate rows are accumulated in phase order.  Ids grow with the
             // key (group, patch, phase), so the previous phase of the same (group, patch) is the previous id.
             for (uint32_t id = 1; id < n_mt; ++id) {
@@ -1035,7 +1037,7 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
                 unsigned int *row = dep_h.data() + (size_t)id * kMaxPatchDeps;
                 uint32_t k = 0;
                 while (k < kMaxPatchDeps && row[k] != kEmptyDep && row[k] != id - 1) ++k;
-                if (k == kMaxPatchDeps) throw PatchUnsupported("a macro-tile has more than 32 upwind macro-tiles");
+                if (k == kMaxPatchDeps) throw PatchUnsupported("a macro-tile has more than 64 upwind macro-tiles");
                 row[k] = id - 1;
             }
             cuda_ok(cudaMemcpyAsync(dep_tab.p, dep_h.data(), sizeof(unsigned int) * dep_h.size(), cudaMemcpyHostToDevice, stream), "copy dep_tab2");

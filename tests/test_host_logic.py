@@ -208,7 +208,7 @@ def test_patch_levels_kahn_over_the_quotient_graph():
     lib = capi.load()
     n, empty = 4, 0xFFFFFFFF
     P = n ** 3
-    dep = np.full((2, P, 32), empty, dtype=np.uint32)
+    dep = np.full((2, P, 64), empty, dtype=np.uint32)   # 64 slots per macro-tile (kMaxPatchDeps)
     idx = lambda i, j, k: (i * n + j) * n + k   # noqa: E731
     for i in range(n):
         for j in range(n):
