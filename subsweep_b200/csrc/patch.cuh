@@ -953,7 +953,10 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
         } else {
             // The patch graph of some group is cyclic (a jagged Voronoi patch boundary carries flux both ways for
             // directions nearly parallel to it).  Split the macro-tiles into phases (see p_phase_kernel).
-            if (!env_u32("SSW_PATCH_PHASES", 1))
+            // Opt-in (SSW_PATCH_PHASES=1): correct (tests/test_gpu_patch.py) but not yet profitable -- with the simple
+            // lattice order used for pi a 32^3 Voronoi box needs 137 phases and 581 dependent macro-tile levels, more
+            // than its 525 wavefront levels (6.1 ms against 2.4 ms for the level-barrier stream).
+            if (!env_u32("SSW_PATCH_PHASES", 0))
                 throw PatchUnsupported("patches depend on each other cyclically for a direction group");
             if (!level_off_host || level_off_host->size() != (size_t)n_levels + 1)
                 throw PatchUnsupported("cyclic patch graph and no host copy of the level offsets");
