@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Offline study (CPU, numpy) for DESIGN.md section 5.3: how many phases / dependent macro-tile levels does the patch
 form with phases need on a Voronoi grid, for different patch orders pi and patch sizes?  Pure graph arithmetic on the
-flat grid; no GPU.  usage: python tools/phase_study.py [cells_per_dim] [patch_cells]"""
+flat grid; no GPU.  usage: python tools/phase_study.py [cells_per_dim] [patch_cells] [lattice jitter; default: Poisson points]"""
 import ctypes as C
 import sys
 
@@ -22,10 +22,15 @@ def longest_path_levels(src, dst, n):
         lvl = new
 
 
-def study(n=14, patch_cells=64, n_dirs=84, seed=1338):
+def study(n=14, patch_cells=64, n_dirs=84, seed=1338, jitter=None):
     rng = np.random.default_rng(seed)
     box = 1.0
-    pts = rng.uniform(0.0, box, size=(n ** 3, 3))
+    if jitter is None:        # Poisson-Voronoi
+        pts = rng.uniform(0.0, box, size=(n ** 3, 3))
+    else:                     # jittered lattice (the Voronoi variant of the headline box, SURVEY.md 8d config 2: jitter 0.35)
+        h = box / n
+        i, j, k = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+        pts = (np.stack([i, j, k], axis=-1).reshape(-1, 3) + 0.5 + jitter * rng.uniform(-1.0, 1.0, size=(n ** 3, 3))) * h
     g = G.voronoi(pts, box, periodic=True)
     N = g.n_cells
     lib = capi.load()
@@ -84,7 +89,8 @@ def study(n=14, patch_cells=64, n_dirs=84, seed=1338):
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 14
     pc = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-    N, P, rows = study(n, pc)
+    jit = float(sys.argv[3]) if len(sys.argv) > 3 else None
+    N, P, rows = study(n, pc, jitter=jit)
     print(f"{N} Voronoi cells, {P} patches of ~{pc} cells; per direction: wavefront levels | (phases, macro-tiles, macro-tile levels) per patch order")
     for r in rows:
         print(r)
