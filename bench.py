@@ -37,14 +37,14 @@ UNIT = "updates/s"
 # ---------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------
-def build_front_workload(n: int, n_dirs: int, n_levels: int):
+def build_front_workload(n: int, n_dirs: int, n_levels: int, cell_scale: float = 1.0):
     """chemistry-stiff ionization front.  n^3 Cartesian box, non-periodic,
     dense neutral slab x in [0.25, 0.75] (n_H = 1 cm^-3, elsewhere 1e-4), one 5e54 /s source at the centre of
     the -x face."""
     from subsweep_b200 import SweepParameters, grid as G
     from subsweep_b200 import units as U
 
-    cell = 10.0 * U.MEGAPARSEC / 128.0
+    cell = cell_scale * 10.0 * U.MEGAPARSEC / 128.0   # cell_scale < 1: the same photons meet fewer atoms, the front crosses the slab
     g = G.cartesian((n, n, n), cell * n, periodic=False)
     ix = np.arange(g.n_cells) // (n * n)
     slab = (ix >= n // 4) & (ix < 3 * n // 4)
@@ -59,13 +59,13 @@ def build_front_workload(n: int, n_dirs: int, n_levels: int):
     return params, g, fields
 
 
-def build_workload(n: int, grid_kind: str, n_dirs: int, n_levels: int, workload: str = "box"):
+def build_workload(n: int, grid_kind: str, n_dirs: int, n_levels: int, workload: str = "box", front_scale: float = 1.0):
     """SURVEY.md section 8d config 2 at n^3 cells (cell size fixed at 10 Mpc / 128)."""
     from subsweep_b200 import SweepParameters, grid as G
     from subsweep_b200 import units as U
 
     if workload == "front":
-        return build_front_workload(n, n_dirs, n_levels)
+        return build_front_workload(n, n_dirs, n_levels, front_scale)
     cell = 10.0 * U.MEGAPARSEC / 128.0
     box = cell * n
     if grid_kind == "cartesian":
@@ -207,11 +207,12 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arms (the oracle; the only place bench.py touches oracle/)
 # ---------------------------------------------------------------------------------------------
-def cpu_run(n: int, grid_kind: str, n_dirs: int, n_levels: int, steps: int, warmup: int, threads: int, workload: str = "box"):
+def cpu_run(n: int, grid_kind: str, n_dirs: int, n_levels: int, steps: int, warmup: int, threads: int, workload: str = "box",
+            front_scale: float = 1.0):
     """The CPU restatement of the reference algorithm (oracle/, kind "port") on a bounded sample
     of the workload: the same box at n^3 cells.  Returns (updates/s, ms per step, sample text)."""
     import oracle
-    params, g, f = build_workload(n, grid_kind, n_dirs, n_levels, workload)
+    params, g, f = build_workload(n, grid_kind, n_dirs, n_levels, workload, front_scale)
     s = oracle.OracleSweep(params, g, **f, periodic_mode=oracle.PERIODIC_LAGGED)
     for _ in range(n_levels):          # spin-up: unlock all timestep levels (same as the GPU arm)
         s.run_sweeps_threads(threads)
@@ -299,7 +300,7 @@ def run_b200(args) -> None:
     if world > 1:
         dist.barrier()
 
-    params, g, fields = build_workload(args.n, args.grid, args.dirs, args.levels, args.workload)
+    params, g, fields = build_workload(args.n, args.grid, args.dirs, args.levels, args.workload, args.front_scale)
     allreduce = make_allreduce(device) if world > 1 else None
     collectives = make_collectives(device) if world > 1 and not os.environ.get("SSW_BENCH_REPLICATED_CHEMISTRY") else None
     shard_rank, shard_world = rank, world
@@ -360,6 +361,12 @@ def run_b200(args) -> None:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": dev_ms / args.steps,
                               "all_cells_sweep_ms": tim["kernel_level_ms"][lvl0] / max(1, tim["kernel_level_launches"][lvl0]),
                               "sweep_ms": tim["sweep_ms"] / args.steps, "chemistry_ms": tim["chemistry_ms"] / args.steps,
+                              "schedule_ms": tim["schedule_ms"] / args.steps, "update_levels_ms": tim["update_levels_ms"] / args.steps,
+                              "allreduce_ms": tim["allreduce_ms"] / args.steps,
+                              "sweep_level_ms": [v / args.steps for v in tim["sweep_level_ms"][:args.levels]],
+                              "level_counts": [int(v) for v in sweep.level_counts()],
+                              "chem_attempts": sweep.stat("chem_attempts"), "chem_cells": sweep.stat("chem_cells"),
+                              "chem_max_depth": sweep.stat("chem_max_depth"), "schedule_builds": sweep.stat("schedule_builds"),
                               "all_cells_form": "patch dataflow" if sweep.stat("patch_macro_tiles") else "level-barrier stream (" + (sweep.patch_note() or "patch form off") + ")",
                               "macro_tiles": sweep.stat("patch_macro_tiles"), "patch_levels": sweep.stat("patch_levels"),
                               "patch_phases": sweep.stat("patch_phases"),
@@ -488,6 +495,8 @@ def main() -> None:
     ap.add_argument("--levels", type=int, default=4)
     ap.add_argument("--workload", choices=("box", "front"), default="box",
                     help="box: BASELINE.json configs[1] (default); front: configs[3], the chemistry-stiff ionization front")
+    ap.add_argument("--front-scale", type=float, default=1.0,
+                    help="front workload: cell size factor (1 = SURVEY.md config 4; 0.03: the front crosses into the slab)")
     ap.add_argument("--cpu-n", type=int, default=96, help="cells per dimension of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--emulate-shard", type=int, default=0, metavar="W",

@@ -16,6 +16,9 @@ HEADERS = [CSRC / "kernels.cuh", CSRC / "stream.cuh", CSRC / "patch.cuh", CSRC /
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
+    # the reference (Rust) never contracts a*b+c into an FMA and the oracle is built with -ffp-contract=off:
+    # keep every product and sum separately rounded so substep decisions and level rules see the same bits
+    "-fmad=false",
     "-Xcompiler", "-fPIC", "-shared",
 ]
 

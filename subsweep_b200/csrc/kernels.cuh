@@ -31,7 +31,6 @@ namespace ssw {
 namespace cg = cooperative_groups;
 
 constexpr int kMaxDirs = 128;
-__constant__ double c_dirs[kMaxDirs * 3];  // this rank's directions, local order
 
 struct GridView {
     const double4 *face_geo;
@@ -39,6 +38,7 @@ struct GridView {
     const int32_t *face_nb;
     const uint8_t *face_kind;
     const uint32_t *face_off;
+    const double *dirs;   // this rank's directions, local order, 3 per direction (per handle: several handles may share a process)
     uint32_t n_cells;
 };
 
@@ -127,7 +127,7 @@ init_counts_kernel(GridView g, const uint8_t *__restrict__ level, int cur,
     int m = 0;
     if (valid) {
         c = act_list ? act_list[k] : k;
-        const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+        const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
         const uint32_t f0 = g.face_off[c], f1 = g.face_off[c + 1];
         for (uint32_t f = f0; f < f1; ++f) {
             if (g.face_kind[f] != 0) continue;  // only Local faces carry dependencies
@@ -172,9 +172,9 @@ __device__ __forceinline__ void solve_task(const SweepArgs &a, uint32_t task, ui
     if (valid) {
         dl = task / N;
         c = task - dl * N;
-        dx = c_dirs[3 * dl];
-        dy = c_dirs[3 * dl + 1];
-        dz = c_dirs[3 * dl + 2];
+        dx = a.g.dirs[3 * dl];
+        dy = a.g.dirs[3 * dl + 1];
+        dz = a.g.dirs[3 * dl + 2];
         f0 = a.g.face_off[c];
         f1 = a.g.face_off[c + 1];
     }
@@ -340,7 +340,7 @@ mini_count_kernel(GridView g, const uint32_t *__restrict__ tasks, uint32_t n_tas
     if (i >= n_tasks) return;
     const uint32_t t = tasks[i];
     const uint32_t dl = t / g.n_cells, c = t - dl * g.n_cells;
-    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
     uint32_t m = 0;
     for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f)
         if (g.face_kind[f] == 0 && dot_dir(ld_geo(g.face_geo + f), dx, dy, dz) < 0.0) ++m;
@@ -356,7 +356,7 @@ mini_fill_kernel(GridView g, StateView st, const uint32_t *__restrict__ tasks, u
     const uint32_t t = tasks[i];
     const uint32_t N = g.n_cells;
     const uint32_t dl = t / N, c = t - dl * N;
-    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
     uint32_t e = off[i];
     double ttot = 0.0;
     for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
@@ -528,7 +528,7 @@ periodic_gather_kernel(GridView g, const uint32_t *__restrict__ pcells, uint32_t
         p = k;
         c = pcells[p];
     }
-    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
     double acc = 0.0;
     for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
         if (g.face_kind[f] != 2) continue;
@@ -547,7 +547,7 @@ dir_state_kernel(GridView g, StateView st, int which, int n_local_dirs,
     if (c >= g.n_cells) return;
     double total = 0.0;
     for (int dl = 0; dl < n_local_dirs; ++dl) {
-        const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+        const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
         double acc = 0.0, ttot = 0.0;
         for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
             const double4 geo = ld_geo(g.face_geo + f);
@@ -587,7 +587,7 @@ photon_patch_kernel(GridView g, StateView st, const uint32_t *__restrict__ touch
     const uint32_t c = touch_list[blockIdx.x];
     const int dl = threadIdx.x;
     if (dl < n_local_dirs) {
-        const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+        const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
         double acc = 0.0;
         constexpr int kChunk = 8;
         const uint32_t f0 = g.face_off[c], f1 = g.face_off[c + 1];

@@ -165,7 +165,7 @@ p_edges_kernel(GridView g, uint32_t n_dl, const uint32_t *__restrict__ patch_of,
     if (t >= (size_t)g.n_cells * n_dl) return;
     const uint32_t dl = (uint32_t)(t / g.n_cells), c = (uint32_t)(t - (size_t)dl * g.n_cells);
     const uint32_t pc = patch_of[c];
-    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
     unsigned int *row = dep_tab + ((size_t)group_of[dl] * n_patches + pc) * kMaxPatchDeps;
     for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
         if (g.face_kind[f] != 0) continue;
@@ -198,7 +198,7 @@ p_phase_kernel(GridView g, const uint32_t *__restrict__ tasks, uint32_t s0, uint
     const uint32_t dl = t / N, c = t - dl * N;
     const uint32_t *const pig = pi + (size_t)group_of[dl] * n_patches;
     const uint32_t my_pi = pig[patch_of[c]];
-    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
     uint32_t ph = 0;
     for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
         if (g.face_kind[f] != 0) continue;
@@ -246,7 +246,7 @@ p_edges2_kernel(GridView g, uint32_t n_dl, const uint32_t *__restrict__ patch_of
     const size_t gbase = (size_t)group_of[dl] * n_patches;
     const uint32_t me = mtid_of[(gbase + patch_of[c]) * n_phase + phase[t]];
     atomicMin(minlev + (size_t)me * kd_max + group_rank[dl], tlevel[t]);
-    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
     unsigned int *row = dep_tab + (size_t)me * kMaxPatchDeps;
     for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
         if (g.face_kind[f] != 0) continue;
@@ -327,7 +327,7 @@ p_count_kernel(GridView g, const uint32_t *__restrict__ k32, uint32_t n, uint32_
     const uint32_t c = k / n_dl, dl = k - c * n_dl;
     const uint32_t pc = patch_of[c];
     const uint8_t *const ph = phase ? phase + (size_t)dl * g.n_cells : nullptr;   // phases of this direction's tasks
-    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
     uint32_t m = 0, x = 0, np = 0;
     double ttot = 0.0;
     for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
@@ -457,7 +457,7 @@ p_fill_kernel(PFillArgs a) {
         const uint32_t e0 = (uint32_t)(a.upoff[s] - e_base);
         uint32_t e = e0, n_per = 0;
         uint32_t x = (uint32_t)(a.xoff[s] - a.xoff[mt0]);
-        const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+        const double dx = a.g.dirs[3 * dl], dy = a.g.dirs[3 * dl + 1], dz = a.g.dirs[3 * dl + 2];
         for (int pass = 0; pass < 2; ++pass) {   // Local faces first, then the periodic ones
             for (uint32_t f = a.g.face_off[c]; f < a.g.face_off[c + 1]; ++f) {
                 if (a.g.face_kind[f] != (pass ? 2 : 0)) continue;
@@ -518,7 +518,7 @@ p_periodic_list_kernel(GridView g, const uint32_t *__restrict__ pcells, uint32_t
     const uint32_t f0 = g.face_off[c], f1 = g.face_off[c + 1];
     uint32_t m = fill ? off[p] : 0u;
     for (uint32_t dl = 0; dl < n_dl; ++dl) {
-        const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+        const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
         for (uint32_t f = f0; f < f1; ++f) {
             if (g.face_kind[f] != 2) continue;
             const double dd = dot_dir(ld_geo(g.face_geo + f), dx, dy, dz);

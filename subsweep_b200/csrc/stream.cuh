@@ -60,9 +60,9 @@
 namespace ssw {
 
 constexpr uint32_t kNoDep = 0xffffffffu;
-constexpr int kMaxStreamThreads = 512;
-constexpr int kMaxStages = 4;
-constexpr int kMaxGroups = 8;
+constexpr int kMaxStreamThreads = 1024;
+constexpr int kMaxStages = 8;
+constexpr int kMaxGroups = 8;      // interleaved / dedicated groups; solo mode uses one group per local direction
 constexpr int kGroupShift = 40;   // sort key = group << 40 | (cell * Dl + dl)
 
 struct TileDesc {       // 16 B, one per tile, stored per block in consumption order
@@ -118,6 +118,7 @@ struct Compiled {
     uint32_t n_tiles = 0;
     uint32_t n_lag = 0;             // snapshot slots behind the task slots
     uint32_t threads = 512, bps = 1, n_blocks = 0, stages = 0, stage_bytes = 0;
+    bool solo = false;              // one block per local direction, block barriers only (no level counters)
     uint32_t n_cells = 0, n_periodic = 0;
     uint64_t stream_bytes = 0;
     double mean_entries = 0.0;
@@ -158,6 +159,7 @@ struct Compiled {
         mt_flag = nullptr;
         ptab = nullptr;
         patch_mode = false;
+        solo = false;
         accumulate = false;
         n_phases = 1;
         slot_of = lag_src = tab_off = lvl_target = lvl_dep = nullptr;
@@ -194,7 +196,7 @@ s_epilogue_key_kernel(GridView g, const uint32_t *__restrict__ pcells, uint32_t 
     if (i >= n_periodic * n_dl) return;
     const uint32_t p = i / n_dl, dl = i - p * n_dl;
     const uint32_t c = pcells[p];
-    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
     bool any = false;
     for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f)
         if (g.face_kind[f] == 2 && dot_dir(ld_geo(g.face_geo + f), dx, dy, dz) < 0.0) any = true;
@@ -267,7 +269,7 @@ s_count_kernel(GridView g, const uint32_t *__restrict__ keys, uint32_t n, uint32
     if (s >= n_all) return;
     const uint32_t k = keys[s];
     const uint32_t c = k / n_dl, dl = k - c * n_dl;
-    const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+    const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
     const bool real = s < n;
     uint32_t m = 0, lag = 0, lvl_end = 0;
     double ttot = 0.0;
@@ -387,7 +389,7 @@ s_fill_kernel(FillArgs a) {
         cell[tid] = epilogue ? (uint32_t)a.pidx[c] : c;   // epilogue tiles address acc_per by periodic row
         const uint32_t e0 = (uint32_t)(a.upoff[s] - e_base);
         uint32_t e = e0, n_per = 0;
-        const double dx = c_dirs[3 * dl], dy = c_dirs[3 * dl + 1], dz = c_dirs[3 * dl + 2];
+        const double dx = a.g.dirs[3 * dl], dy = a.g.dirs[3 * dl + 1], dz = a.g.dirs[3 * dl + 2];
         uint32_t lvl_end = 0;
         for (int pass = epilogue ? 1 : 0; pass < 2; ++pass) {   // Local faces first, then the periodic ones
             for (uint32_t f = a.g.face_off[c]; f < a.g.face_off[c + 1]; ++f) {
@@ -555,7 +557,13 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 //   phase 2 (task-parallel)   a thread sums the products of its slot (Local faces in face order, then
 //                             the periodic ones), applies the absorption and stores the outgoing rate;
 //                             the per-cell rate is reduced over the segment with warp shuffles
-template <int THREADS, int MIN_BLOCKS, bool PROFILE>
+//
+// SOLO: the block owns one local direction (group = direction, grid = number of local directions).  Every
+// dependency of a tile was then produced by this very block: a level change is the block barrier behind the
+// previous tile, there are no level counters, the gathers may hit the SM's own L1 (plain loads of values the
+// same SM stored), and every (direction, cell) rate term is written exactly once (plain store, no accumulator
+// read, no segment reduction).
+template <int THREADS, int MIN_BLOCKS, bool PROFILE, bool SOLO>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 sweep_stream_kernel(StreamArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -599,7 +607,7 @@ sweep_stream_kernel(StreamArgs a) {
         if (PROFILE && tid == 0) t_pkt += clock64() - tp;
         unsigned char *const pkt = ring + (size_t)stage * stage_bytes;
         const PacketHeader d = *reinterpret_cast<const PacketHeader *>(pkt);
-        if (d.level != prev_level) {
+        if (!SOLO && d.level != prev_level) {
             __syncthreads();   // every thread has issued all its stores of the previous pseudo-level
             // arrive (thread 0) and wait (thread 32) run side by side; the arrival must not wait for the
             // dependency, or two blocks could wait for each other
@@ -637,7 +645,7 @@ sweep_stream_kernel(StreamArgs a) {
             c = cell[tid];
             inf = info[tid];
             e1 = info[tid + 1] & 0xffffu;
-            if (inf & kInfoHead) acc_old = __ldcg(acc + c);
+            if (!SOLO && (inf & kInfoHead)) acc_old = __ldcg(acc + c);
             if (!epilogue) rec = __ldg(a.cellrec + c);
         }
         // phase 1: four independent gathers per thread and round
@@ -645,10 +653,17 @@ sweep_stream_kernel(StreamArgs a) {
             const uint32_t i1 = i + THREADS, i2 = i + 2u * THREADS, i3 = i + 3u * THREADS;
             const bool p1 = i1 < E, p2 = i2 < E, p3 = i3 < E;
             double v0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-            v0 = __ldcg(out_slot + es[i]);
-            if (p1) v1 = __ldcg(out_slot + es[i1]);
-            if (p2) v2 = __ldcg(out_slot + es[i2]);
-            if (p3) v3 = __ldcg(out_slot + es[i3]);
+            if (SOLO) {   // only this block (this SM) ever stores the slots it gathers: L1 is coherent for them
+                v0 = out_slot[es[i]];
+                if (p1) v1 = out_slot[es[i1]];
+                if (p2) v2 = out_slot[es[i2]];
+                if (p3) v3 = out_slot[es[i3]];
+            } else {
+                v0 = __ldcg(out_slot + es[i]);
+                if (p1) v1 = __ldcg(out_slot + es[i1]);
+                if (p2) v2 = __ldcg(out_slot + es[i2]);
+                if (p3) v3 = __ldcg(out_slot + es[i3]);
+            }
             prod[i] = v0 * prod[i];
             if (p1) prod[i1] = v1 * prod[i1];
             if (p2) prod[i2] = v2 * prod[i2];
@@ -672,8 +687,21 @@ sweep_stream_kernel(StreamArgs a) {
                 const double total = (in_loc + rec.y) + in_per;         // site.rs:49-56
                 // HydrogenOnly::get_outgoing_rate, hydrogen_only/mod.rs:81-87
                 const double out = (total < threshold) ? 0.0 : total * rec.x;
-                __stcg(out_slot + d.slot0 + tid, out);
+                if (SOLO) out_slot[d.slot0 + tid] = out;
+                else __stcg(out_slot + d.slot0 + tid, out);
             }
+        }
+        if (SOLO) {
+            if (tid < n) __stcs(acc + c, inc);   // the one term (direction, cell): read once by s_rate_finish_kernel
+            __syncthreads();   // all threads are done with the stage; the stores above are visible to the block
+            if (tid == 0 && d.next_bytes) {
+                fence_proxy_async_smem();
+                mbar_expect_tx(smem_u32(full + stage), d.next_bytes);
+                tma_bulk_load(smem_u32(pkt), stream + (size_t)d.next_off16 * 16u, d.next_bytes, smem_u32(full + stage),
+                              policy);
+            }
+            if (++stage == stages) { stage = 0; parity ^= 1u; }
+            continue;
         }
         // segmented suffix sums over the lanes of a warp: a lane ends up with the sum of its segment
         // from itself to the segment's end inside the warp
@@ -712,7 +740,7 @@ sweep_stream_kernel(StreamArgs a) {
         if (++stage == stages) { stage = 0; parity ^= 1u; }
     }
     __syncthreads();
-    if (tid == 0 && prev_level != kNoDep) red_release_gpu(a.lvl_count + (size_t)prev_level * kCountStride);
+    if (!SOLO && tid == 0 && prev_level != kNoDep) red_release_gpu(a.lvl_count + (size_t)prev_level * kCountStride);
     if (PROFILE && tid == 0) {
         a.prof[6 * blockIdx.x + 0] = (unsigned long long)(clock64() - t_begin);
         a.prof[6 * blockIdx.x + 1] = (unsigned long long)t_bar;
@@ -725,16 +753,21 @@ sweep_stream_kernel(StreamArgs a) {
 // ---- host side --------------------------------------------------------------------------------------
 typedef void (*StreamKernel)(StreamArgs);
 
-inline StreamKernel stream_kernel_for(uint32_t threads, uint32_t blocks_per_sm, bool profile = false) {
-    if (profile) return threads == 256 ? sweep_stream_kernel<256, 4, true> : sweep_stream_kernel<512, 2, true>;
-    if (threads == 256) {
-        if (blocks_per_sm >= 8) return sweep_stream_kernel<256, 8, false>;
-        if (blocks_per_sm >= 6) return sweep_stream_kernel<256, 6, false>;
-        return sweep_stream_kernel<256, 4, false>;
+inline StreamKernel stream_kernel_for(uint32_t threads, uint32_t blocks_per_sm, bool profile = false, bool solo = false) {
+    if (solo) {
+        if (threads == 1024) return profile ? sweep_stream_kernel<1024, 1, true, true> : sweep_stream_kernel<1024, 1, false, true>;
+        if (threads == 512) return profile ? sweep_stream_kernel<512, 1, true, true> : sweep_stream_kernel<512, 1, false, true>;
+        return profile ? sweep_stream_kernel<256, 1, true, true> : sweep_stream_kernel<256, 1, false, true>;
     }
-    if (blocks_per_sm >= 4) return sweep_stream_kernel<512, 4, false>;
-    if (blocks_per_sm >= 3) return sweep_stream_kernel<512, 3, false>;
-    return sweep_stream_kernel<512, 2, false>;
+    if (profile) return threads == 256 ? sweep_stream_kernel<256, 4, true, false> : sweep_stream_kernel<512, 2, true, false>;
+    if (threads == 256) {
+        if (blocks_per_sm >= 8) return sweep_stream_kernel<256, 8, false, false>;
+        if (blocks_per_sm >= 6) return sweep_stream_kernel<256, 6, false, false>;
+        return sweep_stream_kernel<256, 4, false, false>;
+    }
+    if (blocks_per_sm >= 4) return sweep_stream_kernel<512, 4, false, false>;
+    if (blocks_per_sm >= 3) return sweep_stream_kernel<512, 3, false, false>;
+    return sweep_stream_kernel<512, 2, false, false>;
 }
 
 inline size_t stream_smem_bytes(uint32_t stages, uint32_t stage_bytes) {
@@ -758,7 +791,7 @@ inline uint32_t env_u32(const char *name, uint32_t fallback) {
 inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tasks, const uint32_t *level_off_dev,
                              uint64_t n_tasks, uint32_t n_levels, int n_local_dirs, const uint32_t *pcells,
                              uint32_t n_periodic, const int32_t *pidx, const double *q_nat, int num_sms,
-                             cudaStream_t stream, uint64_t *launch_counter) {
+                             cudaStream_t stream, uint64_t *launch_counter, bool solo_default = false) {
     C.release();
     if (n_tasks >= 0x7fffff00ull) throw std::runtime_error("compile_schedule: more than 2^31 tasks per rank");
     if (n_local_dirs > 128) throw std::runtime_error("compile_schedule: more than 128 local directions");
@@ -769,11 +802,24 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
     // level barriers, fewer and larger blocks with a single direction group cross them fastest (measured at
     // 10 and 21 directions); otherwise 256-thread blocks, 4 per SM, two interleaved groups
     const bool few_dirs = n_dl <= 24;
-    const uint32_t threads = env_u32("SSW_STREAM_THREADS", few_dirs ? 512 : 256) == 256 ? 256u : 512u;
-    uint32_t G = std::min<uint32_t>(env_u32("SSW_STREAM_GROUPS", few_dirs ? 1 : 2), kMaxGroups);
-    G = std::max<uint32_t>(1u, std::min<uint32_t>(G, n_dl));
-    uint32_t want_bps = env_u32("SSW_STREAM_BPS", threads == 256 ? 4 : 2);
-    const uint32_t want_stages = std::max<uint32_t>(1u, std::min<uint32_t>(env_u32("SSW_STREAM_STAGES", 3), kMaxStages));
+    // solo: one block per local direction walks that direction's whole wavefront; block barriers only
+    const bool solo = env_u32("SSW_STREAM_SOLO", solo_default ? 1 : 0) != 0 && n_dl <= (uint32_t)num_sms;
+    uint32_t threads, tile_slots, G, want_bps, want_stages;
+    if (solo) {
+        const uint32_t t = env_u32("SSW_SOLO_THREADS", 1024);
+        threads = t <= 256 ? 256u : (t <= 512 ? 512u : 1024u);
+        tile_slots = std::max<uint32_t>(32u, std::min<uint32_t>(threads, env_u32("SSW_SOLO_TILE", 512)));
+        G = n_dl;
+        want_bps = 1;
+        want_stages = std::max<uint32_t>(1u, std::min<uint32_t>(env_u32("SSW_SOLO_STAGES", 4), kMaxStages));
+    } else {
+        threads = env_u32("SSW_STREAM_THREADS", few_dirs ? 512 : 256) == 256 ? 256u : 512u;
+        tile_slots = threads;
+        G = std::min<uint32_t>(env_u32("SSW_STREAM_GROUPS", few_dirs ? 1 : 2), kMaxGroups);
+        G = std::max<uint32_t>(1u, std::min<uint32_t>(G, n_dl));
+        want_bps = env_u32("SSW_STREAM_BPS", threads == 256 ? 4 : 2);
+        want_stages = std::max<uint32_t>(1u, std::min<uint32_t>(env_u32("SSW_STREAM_STAGES", 3), kMaxStages));
+    }
     const uint32_t n_real_pl = n_levels * G, n_pl = n_real_pl + G;
     const uint32_t n_epi_cand = n_periodic * n_dl;
     const unsigned blocks = (unsigned)((n + 255) / 256);
@@ -869,7 +915,7 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         std::vector<unsigned long long> tentry;
         uint32_t n_tiles = 0;
         auto cut = [&](const uint32_t *pl_max_dev) {
-            s_cut_kernel<<<cut_blocks, 128, 0, stream>>>(keys, pl_off, n_pl, n_dl, threads, pl_max_dev, nullptr, tile_cnt, nullptr);
+            s_cut_kernel<<<cut_blocks, 128, 0, stream>>>(keys, pl_off, n_pl, n_dl, tile_slots, pl_max_dev, nullptr, tile_cnt, nullptr);
             cuda_ok(cudaMemcpyAsync(tcnt.data(), tile_cnt, sizeof(uint32_t) * n_pl, cudaMemcpyDeviceToHost, stream), "copy");
             cuda_ok(cudaStreamSynchronize(stream), "cut sync");
             for (uint32_t l = 0; l < n_pl; ++l) toff[l + 1] = toff[l] + tcnt[l];
@@ -878,7 +924,7 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
             cudaFree(tile_start); tile_start = nullptr;
             cudaFree(tentry_dev); tentry_dev = nullptr;
             cuda_ok(cudaMalloc(&tile_start, sizeof(uint32_t) * ((size_t)n_tiles + 1)), "malloc tile_start");
-            s_cut_kernel<<<cut_blocks, 128, 0, stream>>>(keys, pl_off, n_pl, n_dl, threads, pl_max_dev, tile_off, nullptr, tile_start);
+            s_cut_kernel<<<cut_blocks, 128, 0, stream>>>(keys, pl_off, n_pl, n_dl, tile_slots, pl_max_dev, tile_off, nullptr, tile_start);
             tstart.assign(n_tiles + 1, 0);
             tentry.assign(n_tiles + 1, 0);
             cuda_ok(cudaMalloc(&tentry_dev, sizeof(unsigned long long) * ((size_t)n_tiles + 1)), "malloc tentry");
@@ -896,7 +942,7 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         for (uint32_t t = 0; t < n_tiles; ++t) {
             const uint32_t ns = tstart[t + 1] - tstart[t];
             const unsigned long long E = tentry[t + 1] - tentry[t];
-            if (ns > threads || E > 65535ull)
+            if (ns > tile_slots || E > 65535ull)
                 throw std::runtime_error("compile_schedule: tile too large (more than 65535 upwind entries in one tile)");
             max_bytes = std::max(max_bytes, tile_layout(ns, (uint32_t)E).bytes);
         }
@@ -913,23 +959,25 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
             if (bps == 1) break;
         }
         if (stages < 1) throw std::runtime_error("compile_schedule: a tile packet does not fit in shared memory");
-        StreamKernel kernel = stream_kernel_for(threads, bps);
+        StreamKernel kernel = stream_kernel_for(threads, bps, false, solo);
         const size_t smem = stream_smem_bytes(stages, stage_bytes);
         cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "set max dynamic smem");
         int per_sm = 0;
         cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)threads, smem), "occupancy");
         if (per_sm < 1) throw std::runtime_error("compile_schedule: stream kernel does not fit on an SM");
         uint32_t nb = (uint32_t)std::min<int>(per_sm, (int)bps) * (uint32_t)num_sms;
+        if (solo) nb = G;
         // interleaved (default): every block serves all direction groups in turn -- group A's tiles of level l,
         // group B's tiles of level l, group A's of level l + 1, ... -- so the latency of one group's level
         // barrier hides behind the other groups' tiles.  Otherwise block b is dedicated to group b % G.
-        const bool interleave = env_u32("SSW_STREAM_INTERLEAVE", 1) != 0;
+        const bool interleave = !solo && env_u32("SSW_STREAM_INTERLEAVE", 1) != 0;
         if (!interleave) {
             nb -= nb % G;
             if (nb < G) throw std::runtime_error("compile_schedule: fewer blocks than direction groups");
         }
         const uint32_t nb_g = interleave ? nb : nb / G;
         C.threads = threads;
+        C.solo = solo;
         C.bps = bps;
         C.stages = stages;
         C.stage_bytes = stage_bytes;
@@ -938,12 +986,13 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
             // k tiles per block and level: tile size = ceil(n_l / (nb_g k)) plus one segment of slack for
             // the cuts at segment boundaries, so the level never needs more than nb_g * k tiles
             std::vector<uint32_t> pl_max(n_pl);
+            const uint64_t seg_max = solo ? 1 : n_dl;   // longest run of slots that must stay in one tile
             for (uint32_t pl = 0; pl < n_pl; ++pl) {
                 const uint64_t n_l = pl_off_h[pl + 1] - pl_off_h[pl];
-                const uint64_t k = std::max<uint64_t>(1, (n_l + (uint64_t)nb_g * threads - 1) / ((uint64_t)nb_g * threads));
-                uint64_t sz = (n_l + nb_g * k - 1) / (nb_g * k) + n_dl;
-                sz = std::max<uint64_t>(sz, std::min<uint64_t>(threads, 2 * n_dl + 32));   // tiny levels: few tiles
-                pl_max[pl] = (uint32_t)std::min<uint64_t>(sz, threads);
+                const uint64_t k = std::max<uint64_t>(1, (n_l + (uint64_t)nb_g * tile_slots - 1) / ((uint64_t)nb_g * tile_slots));
+                uint64_t sz = (n_l + nb_g * k - 1) / (nb_g * k) + (solo ? 0 : seg_max);
+                sz = std::max<uint64_t>(sz, std::min<uint64_t>(tile_slots, 2 * seg_max + 32));   // tiny levels: few tiles
+                pl_max[pl] = (uint32_t)std::min<uint64_t>(sz, tile_slots);
             }
             cuda_ok(cudaMalloc(&pl_max_dev, sizeof(uint32_t) * (size_t)n_pl), "malloc pl_max");
             cuda_ok(cudaMemcpyAsync(pl_max_dev, pl_max.data(), sizeof(uint32_t) * (size_t)n_pl, cudaMemcpyHostToDevice, stream), "copy");
@@ -952,7 +1001,7 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
             for (uint32_t t = 0; t < n_tiles && fits; ++t) {
                 const uint32_t ns = tstart[t + 1] - tstart[t];
                 const unsigned long long E = tentry[t + 1] - tentry[t];
-                fits = ns <= threads && E <= 65535ull && tile_layout(ns, (uint32_t)E).bytes <= stage_bytes;
+                fits = ns <= tile_slots && E <= 65535ull && tile_layout(ns, (uint32_t)E).bytes <= stage_bytes;
             }
             if (!fits) cut(nullptr);   // a shifted tile outgrew the ring stage: keep the uniform cut
         }
@@ -1008,7 +1057,7 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         cuda_ok(cudaMalloc(&C.stream_off, sizeof(uint64_t) * ((size_t)nb + 1)), "malloc stream_off");
         cuda_ok(cudaMalloc(&C.lvl_target, sizeof(uint32_t) * (size_t)n_pl), "malloc lvl_target");
         cuda_ok(cudaMalloc(&C.lvl_dep, sizeof(uint32_t) * (size_t)n_pl), "malloc lvl_dep");
-        cuda_ok(cudaMalloc(&C.lvl_count, sizeof(unsigned int) * (size_t)n_pl * kCountStride), "malloc lvl_count");
+        cuda_ok(cudaMalloc(&C.lvl_count, sizeof(unsigned int) * (solo ? (size_t)kCountStride : (size_t)n_pl * kCountStride)), "malloc lvl_count");
         cuda_ok(cudaMalloc(&C.out_slot, sizeof(double) * ((size_t)n + n_lag)), "malloc out_slot");
         cuda_ok(cudaMalloc(&C.lag_src, sizeof(uint32_t) * (size_t)std::max<uint32_t>(n_lag, 1)), "malloc lag_src");
         cuda_ok(cudaMalloc(&C.acc_cell, sizeof(double) * (size_t)G * g.n_cells), "malloc acc_cell");
@@ -1088,8 +1137,10 @@ inline void run_compiled(Compiled &C, const double2 *cellrec, double threshold, 
         cuda_ok(cudaMemsetAsync(prof_dev, 0, sizeof(unsigned long long) * 6 * (size_t)C.n_blocks, stream), "memset prof");
         a.prof = prof_dev;
     }
-    cuda_ok(cudaMemsetAsync(C.lvl_count, 0, sizeof(unsigned int) * (size_t)C.n_pl * kCountStride, stream), "memset lvl_count");
-    cuda_ok(cudaMemsetAsync(C.acc_cell, 0, sizeof(double) * (size_t)C.n_groups * C.n_cells, stream), "memset acc_cell");
+    if (!C.solo) {   // solo: no level counters, and every (direction, cell) term is stored exactly once per sweep
+        cuda_ok(cudaMemsetAsync(C.lvl_count, 0, sizeof(unsigned int) * (size_t)C.n_pl * kCountStride, stream), "memset lvl_count");
+        cuda_ok(cudaMemsetAsync(C.acc_cell, 0, sizeof(double) * (size_t)C.n_groups * C.n_cells, stream), "memset acc_cell");
+    }
     if (C.n_periodic)
         cuda_ok(cudaMemsetAsync(C.acc_per, 0, sizeof(double) * (size_t)C.n_groups * C.n_periodic, stream), "memset acc_per");
     uint64_t launches = 1;
@@ -1097,7 +1148,7 @@ inline void run_compiled(Compiled &C, const double2 *cellrec, double threshold, 
         s_lag_snapshot_kernel<<<(C.n_lag + 255) / 256, 256, 0, stream>>>(C.lag_src, C.n_lag, (uint32_t)C.n_tasks, C.out_slot);
         ++launches;
     }
-    StreamKernel kernel = stream_kernel_for(C.threads, C.bps, prof_dev != nullptr);
+    StreamKernel kernel = stream_kernel_for(C.threads, C.bps, prof_dev != nullptr, C.solo);
     const size_t smem = stream_smem_bytes(C.stages, C.stage_bytes);
     cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "set max dynamic smem");
     void *args[] = {&a};

@@ -121,6 +121,7 @@ struct Sweep {
 
     // grid
     DevBuf<double4> face_geo;
+    DevBuf<double> dirs_dev;       // this rank's directions (3 per direction, local order)
     DevBuf<double> face_rev;
     DevBuf<int32_t> face_nb;
     DevBuf<uint8_t> face_kind;
@@ -187,12 +188,7 @@ struct Sweep {
     }
 
     // ---- helpers ----
-    void bind() {
-        CUDA_CHECK(cudaSetDevice(device));
-        CUDA_CHECK(cudaMemcpyToSymbolAsync(c_dirs, dirs_all.data() + 3 * (size_t)d0,
-                                           sizeof(double) * 3 * (size_t)Dl, 0,
-                                           cudaMemcpyHostToDevice, stream));
-    }
+    void bind() { CUDA_CHECK(cudaSetDevice(device)); }
     void launched(uint64_t n = 1) { stat[SSW_STAT_KERNEL_LAUNCHES] += n; }
     cudaEvent_t get_event() {
         if (!event_pool.empty()) {
@@ -245,6 +241,7 @@ struct Sweep {
         g.face_nb = face_nb.p;
         g.face_kind = face_kind.p;
         g.face_off = face_off.p;
+        g.dirs = dirs_dev.p;
         g.n_cells = N;
         return g;
     }
@@ -410,6 +407,7 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     n_periodic = (uint32_t)pcells_h.size();
 
     // ---- upload ----
+    dirs_dev.alloc(3 * (size_t)Dl); dirs_dev.upload(dirs_all.data() + 3 * (size_t)d0, 3 * (size_t)Dl, stream);
     face_geo.alloc(F); face_geo.upload(geo.data(), F, stream);
     face_rev.alloc(F); face_rev.upload(rev.data(), F, stream);
     face_nb.alloc(F); face_nb.upload(g->face_neighbour, F, stream);
@@ -794,7 +792,8 @@ void Sweep::single_sweep(int cur) {
                 }
                 if (!patched)
                     compile_schedule(S.compiled, grid_view(), S.tasks.p, S.level_off.p, S.n_tasks, S.n_levels, Dl,
-                                     pcells.p, n_periodic, pidx.p, q.p, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES]);
+                                     pcells.p, n_periodic, pidx.p, q.p, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES],
+                                     /*solo_default=*/true);
             } catch (const std::exception &e) {
                 fail(SSW_E_CUDA, "%s", e.what());
             }

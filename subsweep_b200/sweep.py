@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
+import sys
 from dataclasses import dataclass, field
 from pathlib import Path
 from typing import Callable, Optional, Sequence, Union
@@ -104,6 +105,31 @@ def direction_shard(n_dirs: int, world_size: int, rank: int) -> tuple[int, int]:
     return n_dirs * rank // world_size, n_dirs * (rank + 1) // world_size
 
 
+def allreduce_trampoline(fn: AllReduce):
+    """C callback around a Python all-reduce.  An exception must not propagate through C: it is reported on stderr and
+    turned into a non-zero return, which the library maps to SSW_E_COMM."""
+    def trampoline(_ctx, buf, n, stream):
+        try:
+            fn(int(buf), int(n), int(stream) if stream else None)
+            return 0
+        except Exception as exc:   # noqa: BLE001 - reported through the C error path
+            print(f"subsweep_b200: allreduce hook failed: {exc!r}", file=sys.stderr)
+            return -1
+    return capi.ALLREDUCE_FN(trampoline)
+
+
+def collective_trampoline(fn: Collectives):
+    """C callback around a Python reduce-scatter / all-gather (same error contract as allreduce_trampoline)."""
+    def trampoline(_ctx, op, buf, n, stream):
+        try:
+            fn(int(op), int(buf), int(n), int(stream) if stream else None)
+            return 0
+        except Exception as exc:   # noqa: BLE001 - reported through the C error path
+            print(f"subsweep_b200: collective hook failed: {exc!r}", file=sys.stderr)
+            return -1
+    return capi.COLLECTIVE_FN(trampoline)
+
+
 class Sweep:
     """``Sweep<HydrogenOnly>`` behind the C ABI (src/sweep/mod.rs:172-272)."""
 
@@ -182,27 +208,12 @@ class Sweep:
             raise capi.SubsweepError(rc, (self.lib.ssw_last_error() or b"").decode())
 
     def set_allreduce(self, fn: AllReduce) -> None:
-        def trampoline(_ctx, buf, n, stream):
-            try:
-                fn(int(buf), int(n), int(stream) if stream else None)
-                return 0
-            except Exception as exc:  # must not propagate through C
-                import sys
-                print(f"subsweep_b200: allreduce hook failed: {exc!r}", file=sys.stderr)
-                return -1
-        self._cb = capi.ALLREDUCE_FN(trampoline)
+        self._cb = allreduce_trampoline(fn)
         self._check(self.lib.ssw_set_allreduce(self._h, self._cb, None))
 
     def set_collectives(self, fn: Collectives) -> None:
         """Reduce-scatter / all-gather hook (ssw_set_collectives): chemistry sliced by cells instead of replicated."""
-        def trampoline(_ctx, op, buf, n, stream):
-            try:
-                fn(int(op), int(buf), int(n), int(stream) if stream else None)
-                return 0
-            except Exception as exc:   # noqa: BLE001 - reported through the C error path
-                print(f"subsweep_b200: collective hook failed: {exc!r}", file=sys.stderr)
-                return -1
-        self._coll_cb = capi.COLLECTIVE_FN(trampoline)
+        self._coll_cb = collective_trampoline(fn)
         self._check(self.lib.ssw_set_collectives(self._h, self._coll_cb, None))
 
     def close(self) -> None:
@@ -341,6 +352,7 @@ class SweepPlugin:
     rank: int = 0
     world_size: int = 1
     allreduce: Optional[AllReduce] = None
+    collectives: Optional[Collectives] = None
     solver: Optional[Sweep] = field(default=None, init=False)
     is_first_time: bool = field(default=True, init=False)
     simulation_time: float = field(default=0.0, init=False)
@@ -350,7 +362,8 @@ class SweepPlugin:
                             components["ionized_hydrogen_fraction"], components["temperature"],
                             components["source"], scale_factor=self.scale_factor,
                             device_id=self.device_id, rank=self.rank, world_size=self.world_size,
-                            allreduce=self.allreduce)
+                            allreduce=self.allreduce, collectives=self.collectives,
+                            positions=components.get("position", "grid"))
         n = grid.n_cells
         components.setdefault("photon_rate", np.zeros(n))
         components.setdefault("timestep", np.zeros(n))

@@ -13,10 +13,15 @@ def pytest_configure(config):
 
 
 def _has_gpu() -> bool:
+    """A CUDA device is visible: asked of the driver itself (libcuda), so the answer does not depend on torch."""
+    import ctypes
     try:
-        import torch
-        return torch.cuda.is_available()
-    except Exception:
+        cuda = ctypes.CDLL("libcuda.so.1")
+        if cuda.cuInit(0) != 0:
+            return False
+        n = ctypes.c_int(0)
+        return cuda.cuDeviceGetCount(ctypes.byref(n)) == 0 and n.value > 0
+    except OSError:
         return False
 
 

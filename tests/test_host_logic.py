@@ -227,3 +227,21 @@ def test_patch_levels_kahn_over_the_quotient_graph():
     dep[1, idx(0, 0, 0), 0] = idx(0, 0, 1)
     dep[1, idx(0, 0, 1), :2] = [idx(1, 0, 1), idx(0, 0, 0)]
     assert lib.ssw_patch_levels(dep.ctypes.data_as(C.POINTER(C.c_uint32)), 2, P, lvl.ctypes.data_as(C.POINTER(C.c_uint32))) == capi.SSW_E_DEADLOCK
+
+
+def test_failing_collective_hooks_return_an_error_code(capsys):
+    """A raising Python hook must come back to C as a non-zero return (the library maps it to SSW_E_COMM), never as
+    an exception swallowed by ctypes with a 0 = success return."""
+    from subsweep_b200.sweep import allreduce_trampoline, collective_trampoline
+
+    def boom(*_a):
+        raise RuntimeError("link down")
+
+    cb = allreduce_trampoline(boom)
+    assert cb(None, None, 4, None) == -1
+    cc = collective_trampoline(boom)
+    assert cc(None, 1, None, 4, None) == -1
+    err = capsys.readouterr().err
+    assert "allreduce hook failed" in err and "collective hook failed" in err
+    ok = allreduce_trampoline(lambda *a: None)
+    assert ok(None, 8, 4, None) == 0
