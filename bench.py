@@ -208,13 +208,14 @@ class ClockSampler:
 # CPU arms (the oracle; the only place bench.py touches oracle/)
 # ---------------------------------------------------------------------------------------------
 def cpu_run(n: int, grid_kind: str, n_dirs: int, n_levels: int, steps: int, warmup: int, threads: int, workload: str = "box",
-            front_scale: float = 1.0):
-    """The CPU restatement of the reference algorithm (oracle/, kind "port") on a bounded sample
-    of the workload: the same box at n^3 cells.  Returns (updates/s, ms per step, sample text)."""
+            front_scale: float = 1.0, spin_up: bool = True):
+    """The CPU restatement of the reference algorithm (oracle/, kind "port"): the workload at n^3 cells on `threads`
+    host threads (direction shards; one thread = the reference's single-rank task queue).  Returns (updates/s, ms per
+    step, sample text, updates)."""
     import oracle
     params, g, f = build_workload(n, grid_kind, n_dirs, n_levels, workload, front_scale)
     s = oracle.OracleSweep(params, g, **f, periodic_mode=oracle.PERIODIC_LAGGED)
-    for _ in range(n_levels):          # spin-up: unlock all timestep levels (same as the GPU arm)
+    for _ in range(n_levels if spin_up else 0):   # spin-up: unlock all timestep levels (same as the GPU arm)
         s.run_sweeps_threads(threads)
     for _ in range(warmup):
         s.run_sweeps_threads(threads)
@@ -225,7 +226,8 @@ def cpu_run(n: int, grid_kind: str, n_dirs: int, n_levels: int, steps: int, warm
     dt = time.perf_counter() - t0
     tasks = s.stat("tasks_solved") - t0_tasks
     sample = (f"{n}^3-cell box of the same workload (cell size, density field statistics, source density, "
-              f"{n_dirs} directions, {n_levels} levels), {warmup} warm-up + {steps} timed run_sweeps calls")
+              f"{n_dirs} directions, {n_levels} levels), {warmup} warm-up + {steps} timed run_sweeps calls on {threads} thread(s)"
+              + ("" if spin_up else ", no level spin-up: the first calls, one all-cells sweep each"))
     return tasks / dt, dt / steps * 1e3, sample, tasks
 
 
@@ -241,12 +243,15 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     threads = host_threads()
-    value, ms, sample, _ = cpu_run(args.cpu_n, args.grid, args.dirs, args.levels, args.steps, args.warmup, threads, args.workload)
+    # the same configuration as the GPU arm (args.n cells per dimension) unless --cpu-n bounds the sample further
+    n = args.cpu_n or args.n
+    value, ms, sample, _ = cpu_run(n, args.grid, args.dirs, args.levels, args.steps, args.warmup, threads, args.workload,
+                                   args.front_scale)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, note="CPU arm runs a bounded sample: " + sample),
+        "config": workload_config(args, note=None if n == args.n else "CPU arm runs a bounded sample: " + sample),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -448,8 +453,14 @@ def run_b200(args) -> None:
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
-        v, _, sample, _ = cpu_run(args.cpu_n, args.grid, args.dirs, args.levels, 2, args.warmup, threads, args.workload)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        # bounded sample (about 30 s of CPU work): the same configuration, one warm-up and two timed steps on all host
+        # threads; plus the single-core number (one thread = the reference on one rank) on a 64^3 box of the workload
+        v, _, sample, _ = cpu_run(args.cpu_n or args.n, args.grid, args.dirs, args.levels, 2, 1, threads, args.workload,
+                                  args.front_scale)
+        v1, _, sample1, _ = cpu_run(min(64, args.n), args.grid, args.dirs, args.levels, 2, 0, 1, args.workload,
+                                    args.front_scale, spin_up=False)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                        "single_core": {"value": v1, "unit": UNIT, "cores": 1, "sample": sample1}}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -497,7 +508,8 @@ def main() -> None:
                     help="box: BASELINE.json configs[1] (default); front: configs[3], the chemistry-stiff ionization front")
     ap.add_argument("--front-scale", type=float, default=1.0,
                     help="front workload: cell size factor (1 = SURVEY.md config 4; 0.03: the front crosses into the slab)")
-    ap.add_argument("--cpu-n", type=int, default=96, help="cells per dimension of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=0,
+                    help="cells per dimension of the CPU arm (default 0: the same configuration as the GPU arm, --n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--emulate-shard", type=int, default=0, metavar="W",
                     help="profiling only: run rank 0's direction shard of a W-rank job on one GPU (no-op all-reduce)")

@@ -152,6 +152,29 @@ int ssw_set_collectives(ssw_handle *h, ssw_collective_fn fn, void *ctx);
 int ssw_set_cell_positions(ssw_handle *h, const double *xyz /* N x 3 */);
 const char *ssw_patch_note(ssw_handle *h);
 
+/* -- direction sharding without hooks: peer-mapped exchange over NVLink / NVSwitch ---------------------- */
+
+/* The preferred way to run W ranks on one box (one ssw_handle per GPU).  Every handle owns an ARENA (one device
+ * allocation) with its per-cell state and receive buffers; once the arenas of all ranks are attached the library moves
+ * the per-cell rate partials, absorption factors and timestep levels itself, fused into its kernels as remote stores /
+ * loads over NVLink with flag words for ordering -- no hook, no collective library, nothing of the host on the path
+ * (DESIGN.md section 7).  This replaces SweepCommunicator (src/sweep/communicator.rs:59-95) on the single box.
+ *
+ *   several processes (one per GPU):  ssw_peer_export on every rank -> the host all-gathers the W handles of
+ *       SSW_PEER_HANDLE_BYTES bytes each (MPI_Allgather in the reference's world) -> ssw_peer_attach_ipc;
+ *   one process driving several handles:  ssw_peer_arena on every handle -> ssw_peer_attach with the W base pointers.
+ *
+ * Attach once, after ssw_create and before the first sweep, on every rank.  With peers attached every rank must make
+ * the same sequence of ssw_run_sweeps / ssw_single_sweep / ssw_update_timestep_levels calls, and of ssw_read calls
+ * for SSW_F_PHOTON_RATE and the optional chemistry outputs (they sum over all directions); the other fields may be
+ * read by any single rank at any time between steps.  Cell state is held by the rank that owns the cell
+ * (contiguous slices of ceil(N / W) cells); ssw_read assembles it on the reading rank. */
+#define SSW_PEER_HANDLE_BYTES 64
+int ssw_peer_arena(ssw_handle *h, void **base, uint64_t *bytes);
+int ssw_peer_export(ssw_handle *h, void *ipc_handle_out /* SSW_PEER_HANDLE_BYTES */);
+int ssw_peer_attach_ipc(ssw_handle *h, const void *ipc_handles /* world_size x SSW_PEER_HANDLE_BYTES, rank order */);
+int ssw_peer_attach(ssw_handle *h, void *const *arena_bases /* world_size device pointers, rank order */);
+
 /* -- the hot path ------------------------------------------------------------------------ */
 
 /* Sweep::run_sweeps (src/sweep/mod.rs:258-272): all single sweeps of one full step in the

@@ -75,6 +75,7 @@ class TimeSeries(C.Structure):
         "weighted_photoionization_rate_volume_average", "total_mass", "total_volume")]
 
 
+PEER_HANDLE_BYTES = 64
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)
 COLLECTIVE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p)
 COLL_REDUCE_SCATTER, COLL_ALL_GATHER = 1, 2
@@ -86,6 +87,10 @@ SYMBOLS = {
     "ssw_destroy": (None, [H]),
     "ssw_set_allreduce": (C.c_int, [H, ALLREDUCE_FN, C.c_void_p]),
     "ssw_set_collectives": (C.c_int, [H, COLLECTIVE_FN, C.c_void_p]),
+    "ssw_peer_arena": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "ssw_peer_export": (C.c_int, [H, C.c_void_p]),
+    "ssw_peer_attach_ipc": (C.c_int, [H, C.c_void_p]),
+    "ssw_peer_attach": (C.c_int, [H, C.POINTER(C.c_void_p)]),
     "ssw_set_cell_positions": (C.c_int, [H, c_double_p]),
     "ssw_patch_note": (C.c_char_p, [H]),
     "ssw_run_sweeps": (C.c_int, [H, c_double_p]),

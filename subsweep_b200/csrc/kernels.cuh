@@ -31,6 +31,10 @@ namespace ssw {
 namespace cg = cooperative_groups;
 
 constexpr int kMaxDirs = 128;
+// opt-in shared memory per block on sm_100 (227 KB).  The limit is a per-function attribute of the whole process: it is
+// always raised to the maximum, never to the size of one launch, so that handles on different threads cannot lower it
+// under each other's launches.
+constexpr int kMaxDynamicSmem = 227 * 1024;
 
 struct GridView {
     const double4 *face_geo;
@@ -689,15 +693,37 @@ struct ChemStats {
     unsigned int max_depth;
 };
 
+// Direction sharding over peer-mapped memory (peer.cuh): the chemistry of a cell runs on its owner only.  The rate is
+// the sum of the W partials the ranks stored into the owner's receive buffer, folded in rank order; the new absorption
+// factor goes to the `att` array of every rank.
+struct PeerChem {
+    int32_t world;              // 0 / 1: not sharded this way
+    uint32_t first, n_own, n_per;
+    const double *recv;         // W x n_per partial rates of the own slice
+    double *att[16];            // the att array of every rank
+};
+
 __global__ void __launch_bounds__(128)
 chemistry_kernel(CellView cv, const uint32_t *__restrict__ act_list, uint32_t n_act,
-                 const double *__restrict__ rate_act, ChemParams cp, ChemStats *stats, uint32_t first_cell) {
+                 const double *__restrict__ rate_act, ChemParams cp, ChemStats *stats, uint32_t first_cell, PeerChem pc) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long attempts = 0;
-    unsigned int depth = 0, failed = 0;
-    if (k < n_act) {
-        const uint32_t c = act_list ? act_list[k] : first_cell + k;   // no list: the contiguous cells [first_cell, first_cell + n_act)
-        const double rate = rate_act[k];
+    unsigned int depth = 0, failed = 0, mine = 0;
+    bool active = k < n_act;
+    uint32_t c = 0;
+    if (active) {
+        c = act_list ? act_list[k] : first_cell + k;   // no list: the contiguous cells [first_cell, first_cell + n_act)
+        if (pc.world > 1 && (c < pc.first || c >= pc.first + pc.n_own)) active = false;   // another rank owns the cell
+    }
+    if (active) {
+        mine = 1;
+        double rate;
+        if (pc.world > 1) {
+            rate = 0.0;
+            for (int p = 0; p < pc.world; ++p) rate += pc.recv[(size_t)p * pc.n_per + (c - pc.first)];
+        } else {
+            rate = rate_act[k];
+        }
         const int lvl = cv.level[c];
         const double timestep = cp.max_timestep * exp2(-(double)lvl);  // max_timestep * 0.5^level (exact)
         double relative_change;
@@ -724,7 +750,12 @@ chemistry_kernel(CellView cv, const uint32_t *__restrict__ act_list, uint32_t n_
         cv.x[c] = s.xhii;
         cv.ts[c] = r.timescale;
         cv.tau[c] = (rate_timescale < r.timescale) ? rate_timescale : r.timescale;  // Timescale::min
-        cv.att[c] = non_absorbed_fraction(s.density, s.xhii, s.length);
+        const double att = non_absorbed_fraction(s.density, s.xhii, s.length);
+        if (pc.world > 1) {
+            for (int p = 0; p < pc.world; ++p) pc.att[p][c] = att;
+        } else {
+            cv.att[c] = att;
+        }
         attempts = r.attempts;
         depth = (unsigned)r.max_depth;
         failed = (unsigned)r.failed;
@@ -737,20 +768,20 @@ chemistry_kernel(CellView cv, const uint32_t *__restrict__ act_list, uint32_t n_
     for (int o = 16; o > 0; o >>= 1) {
         attempts += __shfl_down_sync(0xffffffffu, attempts, o);
         failed += __shfl_down_sync(0xffffffffu, failed, o);
+        mine += __shfl_down_sync(0xffffffffu, mine, o);
         depth = max(depth, __shfl_down_sync(0xffffffffu, depth, o));
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&s_att, attempts);
         atomicAdd(&s_fail, (unsigned long long)failed);
+        atomicAdd(&s_cells, (unsigned long long)mine);
         atomicMax(&s_depth, depth);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t first = blockIdx.x * blockDim.x;
-        const uint32_t n_here = first < n_act ? min(blockDim.x, n_act - first) : 0;
+    if (threadIdx.x == 0 && s_cells) {
         atomicAdd(&stats->attempts, s_att);
         atomicAdd(&stats->failures, s_fail);
-        atomicAdd(&stats->cells, (unsigned long long)n_here);
+        atomicAdd(&stats->cells, s_cells);
         atomicMax(&stats->max_depth, s_depth);
     }
 }
@@ -810,20 +841,31 @@ __host__ __device__ inline int level_rule(int max_num_levels, double max_timeste
     return level;
 }
 
+// `first` / `n`: the cells [first, first + n) (all cells, or the slice this rank owns); with peers the new level is
+// stored into the level array of every rank (peer.cuh)
+struct PeerLevels {
+    int32_t world;
+    uint8_t *level[16];
+};
 __global__ void __launch_bounds__(256)
-levels_kernel(const double *__restrict__ tau, uint8_t *__restrict__ level, uint32_t n, int n_levels,
+levels_kernel(const double *__restrict__ tau, uint8_t *__restrict__ level, uint32_t first, uint32_t n, int n_levels,
               double max_timestep, double safety, int lowest_allowed,
-              unsigned long long *__restrict__ hist /* 32 counts + [32] = number of changed cells */) {
+              unsigned long long *__restrict__ hist /* 32 counts + [32] = number of changed cells */, PeerLevels pl) {
     __shared__ unsigned int s_hist[32];
     if (threadIdx.x < 32) s_hist[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = first + k;
     bool changed = false;
-    if (c < n) {
+    if (k < n) {
         int lv = level_rule(n_levels, max_timestep, safety * tau[c]);
         if (lv < lowest_allowed) lv = lowest_allowed;
         if (level[c] != (uint8_t)lv) {
-            level[c] = (uint8_t)lv;
+            if (pl.world > 1) {
+                for (int p = 0; p < pl.world; ++p) pl.level[p][c] = (uint8_t)lv;
+            } else {
+                level[c] = (uint8_t)lv;
+            }
             changed = true;
         }
         atomicAdd(&s_hist[lv], 1u);
@@ -846,9 +888,9 @@ histogram_kernel(const uint8_t *__restrict__ level, uint32_t n, unsigned long lo
 
 // ionization_time (src/sweep/mod.rs:731-738): first time xHII > 0.5; +inf = IonizationTime::default() = not yet
 __global__ void __launch_bounds__(256)
-ionization_time_kernel(const double *__restrict__ x, double *__restrict__ ion_time, uint32_t n, double now) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n && x[c] > 0.5 && isinf(ion_time[c])) ion_time[c] = now;
+ionization_time_kernel(const double *__restrict__ x, double *__restrict__ ion_time, uint32_t first, uint32_t n, double now) {
+    const uint32_t c = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < first + n && x[c] > 0.5 && isinf(ion_time[c])) ion_time[c] = now;
 }
 
 // optional chemistry outputs, src/sweep/chemistry_output.rs:25-55 with Sweep::get_solver (mod.rs:612-632)

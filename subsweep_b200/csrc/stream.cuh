@@ -65,12 +65,14 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxGroups = 8;      // interleaved / dedicated groups; solo mode uses one group per local direction
 constexpr int kGroupShift = 40;   // sort key = group << 40 | (cell * Dl + dl)
 
-struct TileDesc {       // 16 B, one per tile, stored per block in consumption order
+struct TileDesc {       // 20 B, one per tile, stored per block in consumption order
     uint32_t slot0;     // first slot of the tile
     uint32_t off16;     // packet offset inside the block's stream, in 16-B units
     uint16_t n;         // slots in the tile (<= THREADS)
     uint16_t n_entries; // upwind entries in the tile
     uint32_t level;     // pseudo-level
+    uint32_t aux;       // walk form: entries gathered from global memory | epilogue tile << 16
+    uint32_t need;      // walk form: index (in its block) of the first tile of the same pseudo-level
 };
 
 // first 32 bytes of a packet: what the consuming block needs to know about this tile and about
@@ -118,7 +120,9 @@ struct Compiled {
     uint32_t n_tiles = 0;
     uint32_t n_lag = 0;             // snapshot slots behind the task slots
     uint32_t threads = 512, bps = 1, n_blocks = 0, stages = 0, stage_bytes = 0;
-    bool solo = false;              // one block per local direction, block barriers only (no level counters)
+    bool solo = false;              // walk form (walk.cuh): one block per local direction, block barriers only
+    uint32_t window = 0, walk_groups = 1; // walk form: slots of the shared-memory window, compute groups per block
+    uint64_t n_near = 0, n_far = 0; // walk form: upwind entries read from the window / from global memory
     uint32_t n_cells = 0, n_periodic = 0;
     uint64_t stream_bytes = 0;
     double mean_entries = 0.0;
@@ -133,6 +137,8 @@ struct Compiled {
     uint32_t *lvl_target = nullptr; // n_pl: blocks that own a tile of the pseudo-level
     uint32_t *lvl_dep = nullptr;    // n_pl: pseudo-level that must be complete first (kNoDep: none)
     unsigned int *lvl_count = nullptr; // n_pl arrival counters
+    double2 *rec_slot = nullptr;    // walk form: {absorption factor, source / D} per slot, refreshed every sweep
+    uint32_t *cell_of_slot = nullptr; // walk form: n_tasks
     double *acc_cell = nullptr;     // G x N: sum_d incoming of the group's directions
     double *acc_per = nullptr;      // G x n_periodic: sum_d periodic_source (patch mode: one row)
     // patch-ordered form (patch.cuh): macro-tiles (patch, direction group) with point-to-point done flags
@@ -153,6 +159,8 @@ struct Compiled {
     void release() {
         cudaFree(slot_of); cudaFree(out_slot); cudaFree(ttot_slot); cudaFree(lag_src); cudaFree(stream);
         cudaFree(tab); cudaFree(tab_off); cudaFree(stream_off); cudaFree(lvl_target); cudaFree(lvl_dep);
+        cudaFree(rec_slot); cudaFree(cell_of_slot);
+        rec_slot = nullptr; cell_of_slot = nullptr;
         cudaFree(lvl_count); cudaFree(acc_cell); cudaFree(acc_per); cudaFree(mt_flag); cudaFree(ptab); cudaFree(per_off); cudaFree(per_src); cudaFree(per_w);
         per_off = per_src = nullptr;
         per_w = nullptr;
@@ -174,6 +182,12 @@ struct Compiled {
 
 inline bool compiled_supported() { return true; }
 
+// thrown by compile_schedule when the walk form (walk.cuh) cannot hold the grid: the caller compiles the level-barrier
+// stream instead
+struct WalkUnsupported : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
 // ---- construction kernels (run once per compiled schedule) -----------------------------------
 
 // task id (dl * N + c) -> sort key: group << 40 | (c * Dl + dl)
@@ -191,16 +205,18 @@ s_key64_kernel(const uint32_t *__restrict__ tasks, uint32_t n, uint32_t n_cells,
 // upwind face for dl, else ~0 (sorted to the end)
 __global__ void __launch_bounds__(256)
 s_epilogue_key_kernel(GridView g, const uint32_t *__restrict__ pcells, uint32_t n_periodic, uint32_t n_dl,
-                      uint32_t n_groups, unsigned long long *__restrict__ keys) {
+                      uint32_t n_groups, unsigned long long *__restrict__ keys, bool degree_bits = false) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_periodic * n_dl) return;
     const uint32_t p = i / n_dl, dl = i - p * n_dl;
     const uint32_t c = pcells[p];
     const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
-    bool any = false;
+    uint32_t deg = 0;
     for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f)
-        if (g.face_kind[f] == 2 && dot_dir(ld_geo(g.face_geo + f), dx, dy, dz) < 0.0) any = true;
-    keys[i] = any ? (((unsigned long long)(dl % n_groups) << kGroupShift) | (unsigned long long)(c * n_dl + dl))
+        if (g.face_kind[f] == 2 && dot_dir(ld_geo(g.face_geo + f), dx, dy, dz) < 0.0) ++deg;
+    // walk form: slots of a pseudo-level are ordered by degree, descending (walk.cuh)
+    const unsigned long long dbits = degree_bits ? ((unsigned long long)(63u - min(deg, 63u)) << 32) : 0ull;
+    keys[i] = deg ? (((unsigned long long)(dl % n_groups) << kGroupShift) | dbits | (unsigned long long)(c * n_dl + dl))
                   : ~0ull;
 }
 
@@ -551,6 +567,10 @@ struct StreamArgs {
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+}  // namespace ssw
+#include "walk.cuh"
+namespace ssw {
+
 // Persistent kernel: block b consumes the tiles tab[tab_off[b] .. tab_off[b+1]) in order.  Per tile:
 //   phase 1 (entry-parallel)  prod[e] = out_slot[source slot[e]] * share[e], written over share[e] in the
 //                             ring stage: every gather of the tile is independent and in flight at once
@@ -648,6 +668,7 @@ sweep_stream_kernel(StreamArgs a) {
             if (!SOLO && (inf & kInfoHead)) acc_old = __ldcg(acc + c);
             if (!epilogue) rec = __ldg(a.cellrec + c);
         }
+        if (PROFILE && SOLO && tid == 0) tp = clock64();
         // phase 1: four independent gathers per thread and round
         for (uint32_t i = tid; i < E; i += 4u * THREADS) {
             const uint32_t i1 = i + THREADS, i2 = i + 2u * THREADS, i3 = i + 3u * THREADS;
@@ -670,6 +691,7 @@ sweep_stream_kernel(StreamArgs a) {
             if (p3) prod[i3] = v3 * prod[i3];
         }
         __syncthreads();
+        if (PROFILE && SOLO && tid == 0) { const long long now = clock64(); t_bar += now - tp; tp = now; }
         // phase 2
         double inc = 0.0;
         if (tid < n) {
@@ -694,6 +716,7 @@ sweep_stream_kernel(StreamArgs a) {
         if (SOLO) {
             if (tid < n) __stcs(acc + c, inc);   // the one term (direction, cell): read once by s_rate_finish_kernel
             __syncthreads();   // all threads are done with the stage; the stores above are visible to the block
+            if (PROFILE && tid == 0) t_rel += clock64() - tp;
             if (tid == 0 && d.next_bytes) {
                 fence_proxy_async_smem();
                 mbar_expect_tx(smem_u32(full + stage), d.next_bytes);
@@ -754,11 +777,7 @@ sweep_stream_kernel(StreamArgs a) {
 typedef void (*StreamKernel)(StreamArgs);
 
 inline StreamKernel stream_kernel_for(uint32_t threads, uint32_t blocks_per_sm, bool profile = false, bool solo = false) {
-    if (solo) {
-        if (threads == 1024) return profile ? sweep_stream_kernel<1024, 1, true, true> : sweep_stream_kernel<1024, 1, false, true>;
-        if (threads == 512) return profile ? sweep_stream_kernel<512, 1, true, true> : sweep_stream_kernel<512, 1, false, true>;
-        return profile ? sweep_stream_kernel<256, 1, true, true> : sweep_stream_kernel<256, 1, false, true>;
-    }
+    (void)solo;   // the solo form has its own kernel (walk.cuh)
     if (profile) return threads == 256 ? sweep_stream_kernel<256, 4, true, false> : sweep_stream_kernel<512, 2, true, false>;
     if (threads == 256) {
         if (blocks_per_sm >= 8) return sweep_stream_kernel<256, 8, false, false>;
@@ -791,7 +810,7 @@ inline uint32_t env_u32(const char *name, uint32_t fallback) {
 inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tasks, const uint32_t *level_off_dev,
                              uint64_t n_tasks, uint32_t n_levels, int n_local_dirs, const uint32_t *pcells,
                              uint32_t n_periodic, const int32_t *pidx, const double *q_nat, int num_sms,
-                             cudaStream_t stream, uint64_t *launch_counter, bool solo_default = false) {
+                             cudaStream_t stream, uint64_t *launch_counter, bool allow_walk = false) {
     C.release();
     if (n_tasks >= 0x7fffff00ull) throw std::runtime_error("compile_schedule: more than 2^31 tasks per rank");
     if (n_local_dirs > 128) throw std::runtime_error("compile_schedule: more than 128 local directions");
@@ -803,15 +822,19 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
     // 10 and 21 directions); otherwise 256-thread blocks, 4 per SM, two interleaved groups
     const bool few_dirs = n_dl <= 24;
     // solo: one block per local direction walks that direction's whole wavefront; block barriers only
-    const bool solo = env_u32("SSW_STREAM_SOLO", solo_default ? 1 : 0) != 0 && n_dl <= (uint32_t)num_sms;
-    uint32_t threads, tile_slots, G, want_bps, want_stages;
+    const bool solo = allow_walk;
+    uint32_t threads, tile_slots, G, want_bps, want_stages, window = 0, walk_groups = 1, walk_entries = 0;
     if (solo) {
-        const uint32_t t = env_u32("SSW_SOLO_THREADS", 1024);
-        threads = t <= 256 ? 256u : (t <= 512 ? 512u : 1024u);
-        tile_slots = std::max<uint32_t>(32u, std::min<uint32_t>(threads, env_u32("SSW_SOLO_TILE", 512)));
+        // compute groups x threads per group (= slots per tile); the pairs walk_kernel_for knows
+        walk_groups = env_u32("SSW_WALK_GROUPS", 2);
+        threads = env_u32("SSW_WALK_THREADS", 256);
+        if (!walk_kernel_for(walk_groups, threads, false)) { walk_groups = 2; threads = 256; }
+        tile_slots = threads;
+        walk_entries = std::max<uint32_t>(env_u32("SSW_WALK_ENTRIES", 6u * threads), (uint32_t)kWalkMaxDeg);
         G = n_dl;
         want_bps = 1;
-        want_stages = std::max<uint32_t>(1u, std::min<uint32_t>(env_u32("SSW_SOLO_STAGES", 4), kMaxStages));
+        want_stages = std::max<uint32_t>(2u, std::min<uint32_t>(env_u32("SSW_WALK_STAGES", kWalkMaxStages), kWalkMaxStages));
+        window = std::min<uint32_t>(env_u32("SSW_WALK_WINDOW", 16384), 24576u) & ~1023u;
     } else {
         threads = env_u32("SSW_STREAM_THREADS", few_dirs ? 512 : 256) == 256 ? 256u : 512u;
         tile_slots = threads;
@@ -840,7 +863,8 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         // 1. order every level by (group, cell, direction)
         cuda_ok(cudaMalloc(&keys64_in, sizeof(unsigned long long) * (size_t)n), "malloc keys64_in");
         cuda_ok(cudaMalloc(&keys64, sizeof(unsigned long long) * (size_t)n), "malloc keys64");
-        s_key64_kernel<<<blocks, 256, 0, stream>>>(tasks, n, g.n_cells, n_dl, G, keys64_in);
+        if (solo) w_key64_kernel<<<blocks, 256, 0, stream>>>(g, tasks, n, n_dl, keys64_in);
+        else s_key64_kernel<<<blocks, 256, 0, stream>>>(tasks, n, g.n_cells, n_dl, G, keys64_in);
         cuda_ok(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, keys64_in, keys64, (int64_t)n, (int64_t)n_levels,
                                                    level_off_dev, level_off_dev + 1, stream), "segmented sort size");
         cuda_ok(cudaMalloc(&temp, bytes), "malloc sort temp");
@@ -854,7 +878,7 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         cuda_ok(cudaMalloc(&epi_in, sizeof(unsigned long long) * (size_t)std::max<uint32_t>(n_epi_cand, 1)), "malloc epi");
         cuda_ok(cudaMalloc(&epi_sorted, sizeof(unsigned long long) * (size_t)std::max<uint32_t>(n_epi_cand, 1)), "malloc epi");
         if (n_epi_cand) {
-            s_epilogue_key_kernel<<<(n_epi_cand + 255) / 256, 256, 0, stream>>>(g, pcells, n_periodic, n_dl, G, epi_in);
+            s_epilogue_key_kernel<<<(n_epi_cand + 255) / 256, 256, 0, stream>>>(g, pcells, n_periodic, n_dl, G, epi_in, solo);
             cuda_ok(cub::DeviceRadixSort::SortKeys(nullptr, bytes, epi_in, epi_sorted, (int64_t)n_epi_cand, 0, 64, stream), "radix size");
             cuda_ok(cudaMalloc(&temp, bytes), "malloc radix temp");
             cuda_ok(cub::DeviceRadixSort::SortKeys(temp, bytes, epi_in, epi_sorted, (int64_t)n_epi_cand, 0, 64, stream), "radix sort");
@@ -872,6 +896,27 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         if (pl_off_h[n_real_pl] != n) throw std::runtime_error("compile_schedule: pseudo-level offsets inconsistent");
         // 32-bit keys (cell * Dl + dl) of real and epilogue slots
         cuda_ok(cudaMalloc(&keys, sizeof(uint32_t) * (size_t)std::max<uint32_t>(n_all, 1)), "malloc keys");
+        if (solo) {
+            // walk form: renumber the slots direction-major -- pseudo-level (direction g, level l) = g * L + l -- so that a
+            // block's slots are one contiguous range in the order it solves them
+            std::vector<uint32_t> new_off(n_pl + 1), delta(n_real_pl);
+            uint32_t o = 0;
+            for (uint32_t gg = 0; gg < G; ++gg)
+                for (uint32_t l = 0; l < n_levels; ++l) {
+                    new_off[gg * n_levels + l] = o;
+                    delta[l * G + gg] = o - pl_off_h[l * G + gg];   // modulo 2^32
+                    o += pl_off_h[l * G + gg + 1] - pl_off_h[l * G + gg];
+                }
+            for (uint32_t pl = n_real_pl; pl <= n_pl; ++pl) new_off[pl] = pl_off_h[pl];
+            uint32_t *delta_dev = nullptr;
+            cuda_ok(cudaMalloc(&delta_dev, sizeof(uint32_t) * (size_t)std::max<uint32_t>(n_real_pl, 1)), "malloc delta");
+            cuda_ok(cudaMemcpyAsync(delta_dev, delta.data(), sizeof(uint32_t) * (size_t)n_real_pl, cudaMemcpyHostToDevice, stream), "copy delta");
+            w_permute_kernel<<<blocks, 256, 0, stream>>>(keys64, n, pl_off, n_real_pl, delta_dev, keys);
+            cuda_ok(cudaStreamSynchronize(stream), "permute sync");
+            cudaFree(delta_dev);
+            pl_off_h = new_off;
+            cuda_ok(cudaMemcpyAsync(pl_off, pl_off_h.data(), sizeof(uint32_t) * ((size_t)n_pl + 1), cudaMemcpyHostToDevice, stream), "copy pl_off");
+        } else
         s_key32_kernel<<<blocks, 256, 0, stream>>>(keys64, n, keys);
         if (m) s_key32_kernel<<<(m + 255) / 256, 256, 0, stream>>>(epi_sorted, m, keys + n);
         cuda_ok(cudaStreamSynchronize(stream), "key32 sync");
@@ -884,8 +929,8 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         cuda_ok(cudaMalloc(&C.ttot_slot, sizeof(double) * (size_t)n), "malloc ttot_slot");
         cuda_ok(cudaMalloc(&cnt, sizeof(uint32_t) * ((size_t)n_all + 1)), "malloc cnt");
         cuda_ok(cudaMalloc(&upoff, sizeof(unsigned long long) * ((size_t)n_all + 1)), "malloc upoff");
-        cuda_ok(cudaMalloc(&counters, 4 * sizeof(unsigned int)), "malloc counters");
-        cuda_ok(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), stream), "memset");
+        cuda_ok(cudaMalloc(&counters, 8 * sizeof(unsigned int)), "malloc counters");
+        cuda_ok(cudaMemsetAsync(counters, 0, 8 * sizeof(unsigned int), stream), "memset");
         cuda_ok(cudaMemsetAsync(cnt + n_all, 0, sizeof(uint32_t), stream), "memset");
         s_slot_scatter_kernel<<<blocks, 256, 0, stream>>>(keys, n, g.n_cells, n_dl, C.slot_of);
         s_count_kernel<<<(n_all + 255) / 256, 256, 0, stream>>>(g, keys, n, n_all, n_dl, C.slot_of, pl_off, n_pl, cnt,
@@ -915,6 +960,8 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         std::vector<unsigned long long> tentry;
         uint32_t n_tiles = 0;
         auto cut = [&](const uint32_t *pl_max_dev) {
+            if (solo) w_cut_kernel<<<(n_pl + 127) / 128, 128, 0, stream>>>(upoff, pl_off, n_pl, tile_slots, walk_entries, nullptr, tile_cnt, nullptr);
+            else
             s_cut_kernel<<<cut_blocks, 128, 0, stream>>>(keys, pl_off, n_pl, n_dl, tile_slots, pl_max_dev, nullptr, tile_cnt, nullptr);
             cuda_ok(cudaMemcpyAsync(tcnt.data(), tile_cnt, sizeof(uint32_t) * n_pl, cudaMemcpyDeviceToHost, stream), "copy");
             cuda_ok(cudaStreamSynchronize(stream), "cut sync");
@@ -924,6 +971,8 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
             cudaFree(tile_start); tile_start = nullptr;
             cudaFree(tentry_dev); tentry_dev = nullptr;
             cuda_ok(cudaMalloc(&tile_start, sizeof(uint32_t) * ((size_t)n_tiles + 1)), "malloc tile_start");
+            if (solo) w_cut_kernel<<<(n_pl + 127) / 128, 128, 0, stream>>>(upoff, pl_off, n_pl, tile_slots, walk_entries, tile_off, nullptr, tile_start);
+            else
             s_cut_kernel<<<cut_blocks, 128, 0, stream>>>(keys, pl_off, n_pl, n_dl, tile_slots, pl_max_dev, tile_off, nullptr, tile_start);
             tstart.assign(n_tiles + 1, 0);
             tentry.assign(n_tiles + 1, 0);
@@ -939,17 +988,17 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
 
         // 6. launch geometry: stage size = largest packet; blocks per SM and stages from the smem budget
         uint32_t max_bytes = 0;
-        for (uint32_t t = 0; t < n_tiles; ++t) {
+        for (uint32_t t = 0; t < n_tiles && !solo; ++t) {
             const uint32_t ns = tstart[t + 1] - tstart[t];
             const unsigned long long E = tentry[t + 1] - tentry[t];
             if (ns > tile_slots || E > 65535ull)
                 throw std::runtime_error("compile_schedule: tile too large (more than 65535 upwind entries in one tile)");
             max_bytes = std::max(max_bytes, tile_layout(ns, (uint32_t)E).bytes);
         }
-        const uint32_t stage_bytes = std::max<uint32_t>(128u, (max_bytes + 127u) & ~127u);
+        uint32_t stage_bytes = std::max<uint32_t>(128u, (max_bytes + 127u) & ~127u);
         const size_t smem_sm = 227u * 1024u;
         uint32_t bps = std::max<uint32_t>(1u, want_bps), stages = 0;
-        for (;; --bps) {
+        for (; !solo; --bps) {
             const size_t per_block = smem_sm / bps - 1024 - 1024;   // driver reserve + static shared memory
             const size_t fixed = stream_smem_bytes(0, 0);
             if (per_block >= fixed + stage_bytes) {
@@ -958,12 +1007,16 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
             }
             if (bps == 1) break;
         }
-        if (stages < 1) throw std::runtime_error("compile_schedule: a tile packet does not fit in shared memory");
-        StreamKernel kernel = stream_kernel_for(threads, bps, false, solo);
-        const size_t smem = stream_smem_bytes(stages, stage_bytes);
-        cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "set max dynamic smem");
+        if (!solo && stages < 1) throw std::runtime_error("compile_schedule: a tile packet does not fit in shared memory");
         int per_sm = 0;
-        cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)threads, smem), "occupancy");
+        if (solo) {
+            per_sm = 1;   // the ring is sized once the far entries of the tiles are counted (step 7)
+        } else {
+            StreamKernel kernel = stream_kernel_for(threads, bps, false, false);
+            const size_t smem = stream_smem_bytes(stages, stage_bytes);
+            cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem), "set max dynamic smem");
+            cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)threads, smem), "occupancy");
+        }
         if (per_sm < 1) throw std::runtime_error("compile_schedule: stream kernel does not fit on an SM");
         uint32_t nb = (uint32_t)std::min<int>(per_sm, (int)bps) * (uint32_t)num_sms;
         if (solo) nb = G;
@@ -979,10 +1032,10 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         C.threads = threads;
         C.solo = solo;
         C.bps = bps;
-        C.stages = stages;
+        C.stages = stages;            // walk form: set in step 7
         C.stage_bytes = stage_bytes;
         C.n_blocks = nb;
-        if (env_u32("SSW_STREAM_BALANCED", 1)) {
+        if (!solo && env_u32("SSW_STREAM_BALANCED", 1)) {
             // k tiles per block and level: tile size = ceil(n_l / (nb_g k)) plus one segment of slack for
             // the cuts at segment boundaries, so the level never needs more than nb_g * k tiles
             std::vector<uint32_t> pl_max(n_pl);
@@ -1001,7 +1054,7 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
             for (uint32_t t = 0; t < n_tiles && fits; ++t) {
                 const uint32_t ns = tstart[t + 1] - tstart[t];
                 const unsigned long long E = tentry[t + 1] - tentry[t];
-                fits = ns <= tile_slots && E <= 65535ull && tile_layout(ns, (uint32_t)E).bytes <= stage_bytes;
+                fits = ns <= tile_slots && E <= 65535ull && (solo || tile_layout(ns, (uint32_t)E).bytes <= stage_bytes);
             }
             if (!fits) cut(nullptr);   // a shifted tile outgrew the ring stage: keep the uniform cut
         }
@@ -1010,7 +1063,7 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         std::vector<uint32_t> tile_block(n_tiles), tile_level(n_tiles), per_block_count(nb, 0), rr(G, 0);
         uint32_t rr_all = 0;
         for (uint32_t pl = 0; pl < n_pl; ++pl) {
-            const uint32_t grp = pl < n_real_pl ? pl % G : pl - n_real_pl;
+            const uint32_t grp = pl >= n_real_pl ? pl - n_real_pl : (solo ? pl / n_levels : pl % G);
             for (uint32_t t = toff[pl]; t < toff[pl + 1]; ++t) {
                 const uint32_t b = interleave ? (rr_all++ % nb) : grp + (rr[grp]++ % nb_g) * G;
                 tile_block[t] = b;
@@ -1018,22 +1071,81 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
                 per_block_count[b]++;
             }
         }
+        std::vector<uint32_t> tile_far(n_tiles, 0);
+        uint32_t *tile_level_dev = nullptr, *tile_far_dev = nullptr, *tile_start_dev = nullptr;
+        if (solo && n_tiles) {
+            // entries outside the window (gathered from global memory) per tile: sizes the packets and the ring stages
+            cuda_ok(cudaMalloc(&tile_level_dev, sizeof(uint32_t) * (size_t)n_tiles), "malloc tile_level");
+            cuda_ok(cudaMalloc(&tile_far_dev, sizeof(uint32_t) * (size_t)n_tiles), "malloc tile_far");
+            cuda_ok(cudaMalloc(&tile_start_dev, sizeof(uint32_t) * ((size_t)n_tiles + 1)), "malloc tile_start");
+            cuda_ok(cudaMemcpyAsync(tile_level_dev, tile_level.data(), sizeof(uint32_t) * (size_t)n_tiles, cudaMemcpyHostToDevice, stream), "copy");
+            cuda_ok(cudaMemcpyAsync(tile_start_dev, tstart.data(), sizeof(uint32_t) * ((size_t)n_tiles + 1), cudaMemcpyHostToDevice, stream), "copy");
+            WalkFillArgs fa{};
+            fa.g = g; fa.keys = keys; fa.slot_of = C.slot_of; fa.pidx = pidx; fa.upoff = upoff; fa.ttot_slot = C.ttot_slot;
+            fa.pl_off = pl_off; fa.n_pl = n_pl; fa.n_real_pl = n_real_pl; fa.n_dl = n_dl; fa.n_tasks = n; fa.n_levels = n_levels;
+            fa.tile_start = tile_start_dev; fa.tile_level = tile_level_dev; fa.tile_far = tile_far_dev;
+            fa.lag_counter = counters + 1;
+            // The window competes with the ring for shared memory.  The number of ring stages is a multiple of both the
+            // compute groups and the gather warps (a waiter then sees every phase of the mbarriers it waits on: the
+            // previous tile of the same stage was its own), at least groups + 2.  The window shrinks in steps of 2048
+            // slots until that many stages fit; it never goes below what keeps every source outside the usable window
+            // complete in global memory when a tile's gather starts: (stages + 3 groups) tiles.
+            uint32_t unit = walk_groups;
+            while (unit % kWalkGatherWarps) unit += walk_groups;
+            const uint32_t stages_min = ((walk_groups + 2u + unit - 1u) / unit) * unit;
+            const uint32_t window_min = std::max<uint32_t>(2048u, (kWalkMaxStages + 3u * walk_groups) * tile_slots);
+            window = std::max(window, window_min);
+            for (;; window -= 2048u) {
+                fa.window = window;
+                fa.window_usable = window - walk_groups * tile_slots;   // tiles of one level in flight side by side
+                w_fill_kernel<true><<<n_tiles, 512, 0, stream>>>(fa);
+                cuda_ok(cudaMemcpyAsync(tile_far.data(), tile_far_dev, sizeof(uint32_t) * (size_t)n_tiles, cudaMemcpyDeviceToHost, stream), "copy");
+                cuda_ok(cudaStreamSynchronize(stream), "far count sync");
+                uint32_t mx = 0;
+                for (uint32_t t = 0; t < n_tiles; ++t) {
+                    const uint32_t ns = tstart[t + 1] - tstart[t];
+                    const unsigned long long E = tentry[t + 1] - tentry[t];
+                    if (ns > tile_slots || E > 65535ull || tile_far[t] > 65535u) throw WalkUnsupported("walk form: tile too large");
+                    mx = std::max(mx, walk_layout(ns, (uint32_t)E, tile_far[t]).stage_bytes);
+                }
+                stage_bytes = std::max<uint32_t>(128u, (mx + 127u) & ~127u);
+                const size_t per_block = smem_sm - 1024 - 1024;
+                const size_t fixed = walk_smem_bytes(0, 0, window);
+                stages = per_block > fixed ? (uint32_t)std::min<size_t>(want_stages, (per_block - fixed) / stage_bytes) : 0;
+                stages -= stages % unit;
+                if (stages >= stages_min || window < window_min + 2048u) break;
+            }
+            cudaFree(tile_level_dev); cudaFree(tile_far_dev); cudaFree(tile_start_dev);
+            if (stages < unit) throw WalkUnsupported("walk form: too few tile packets fit beside the window");
+            WalkKernel wk = walk_kernel_for(walk_groups, threads, false);
+            const size_t smem = walk_smem_bytes(stages, stage_bytes, window);
+            cuda_ok(cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem), "set max dynamic smem");
+            int occ = 0;
+            cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wk, (int)(walk_groups * threads) + 32 + 32 * kWalkGatherWarps, smem), "occupancy");
+            if (occ < 1) throw WalkUnsupported("walk form: the kernel does not fit on an SM");
+            C.stages = stages;
+            C.stage_bytes = stage_bytes;
+            C.walk_groups = walk_groups;
+        }
         std::vector<uint32_t> tab_off(nb + 1, 0);
         for (uint32_t b = 0; b < nb; ++b) tab_off[b + 1] = tab_off[b] + per_block_count[b];
         std::vector<TileDesc> tab(std::max<uint32_t>(n_tiles, 1));
         std::vector<uint32_t> tab_block_h(std::max<uint32_t>(n_tiles, 1));
         std::vector<uint64_t> stream_off(nb + 1, 0), cursor(nb, 0);
-        std::vector<uint32_t> fill_pos(nb, 0);
+        std::vector<uint32_t> fill_pos(nb, 0), first_of_level(nb, 0), level_of_block(nb, 0xffffffffu);
         for (uint32_t t = 0; t < n_tiles; ++t) {
             const uint32_t b = tile_block[t];
+            if (level_of_block[b] != tile_level[t]) { level_of_block[b] = tile_level[t]; first_of_level[b] = fill_pos[b]; }
             TileDesc d;
+            d.need = first_of_level[b];
             d.slot0 = tstart[t];
             d.n = (uint16_t)(tstart[t + 1] - tstart[t]);
             d.n_entries = (uint16_t)(tentry[t + 1] - tentry[t]);
             d.level = tile_level[t];
+            d.aux = tile_far[t] | (d.level >= n_real_pl ? 1u << 16 : 0u);
             if ((cursor[b] >> 4) > 0xffffffffull) throw std::runtime_error("compile_schedule: block stream exceeds 64 GB");
             d.off16 = (uint32_t)(cursor[b] >> 4);
-            cursor[b] += tile_layout(d.n, d.n_entries).bytes;
+            cursor[b] += solo ? walk_layout(d.n, d.n_entries, tile_far[t]).bytes : tile_layout(d.n, d.n_entries).bytes;
             tab[tab_off[b] + fill_pos[b]] = d;
             tab_block_h[tab_off[b] + fill_pos[b]] = b;
             fill_pos[b]++;
@@ -1042,8 +1154,8 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         C.stream_bytes = stream_off[nb];
         std::vector<uint32_t> lvl_target(n_pl), lvl_dep(n_pl, kNoDep);
         for (uint32_t pl = 0; pl < n_pl; ++pl) lvl_target[pl] = std::min<uint32_t>(tcnt[pl], nb_g);
-        for (uint32_t pl = G; pl < n_real_pl; ++pl) lvl_dep[pl] = pl - G;
-        for (uint32_t grp = 0; grp < G; ++grp) {   // epilogue: behind the group's last non-empty wavefront level
+        for (uint32_t pl = G; pl < n_real_pl && !solo; ++pl) lvl_dep[pl] = pl - G;
+        for (uint32_t grp = 0; grp < G && !solo; ++grp) {   // epilogue: behind the group's last non-empty wavefront level
             for (uint32_t l = n_levels; l-- > 0;) {
                 if (tcnt[l * G + grp] > 0) { lvl_dep[n_real_pl + grp] = l * G + grp; break; }
             }
@@ -1061,6 +1173,11 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         cuda_ok(cudaMalloc(&C.out_slot, sizeof(double) * ((size_t)n + n_lag)), "malloc out_slot");
         cuda_ok(cudaMalloc(&C.lag_src, sizeof(uint32_t) * (size_t)std::max<uint32_t>(n_lag, 1)), "malloc lag_src");
         cuda_ok(cudaMalloc(&C.acc_cell, sizeof(double) * (size_t)G * g.n_cells), "malloc acc_cell");
+        if (solo) {
+            cuda_ok(cudaMalloc(&C.rec_slot, sizeof(double2) * (size_t)std::max<uint32_t>(n, 1)), "malloc rec_slot");
+            cuda_ok(cudaMalloc(&C.cell_of_slot, sizeof(uint32_t) * (size_t)std::max<uint32_t>(n, 1)), "malloc cell_of_slot");
+            w_cell_of_slot_kernel<<<blocks, 256, 0, stream>>>(keys, n, n_dl, C.cell_of_slot);
+        }
         cuda_ok(cudaMalloc(&C.acc_per, sizeof(double) * (size_t)G * std::max<uint32_t>(n_periodic, 1)), "malloc acc_per");
         cuda_ok(cudaMemcpyAsync(C.tab, tab.data(), sizeof(TileDesc) * tab.size(), cudaMemcpyHostToDevice, stream), "copy tab");
         cuda_ok(cudaMemcpyAsync(tab_block, tab_block_h.data(), sizeof(uint32_t) * tab_block_h.size(), cudaMemcpyHostToDevice, stream), "copy");
@@ -1070,7 +1187,15 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         cuda_ok(cudaMemcpyAsync(C.lvl_dep, lvl_dep.data(), sizeof(uint32_t) * (size_t)n_pl, cudaMemcpyHostToDevice, stream), "copy");
 
         // 8. packets and state
-        if (n_tiles) {
+        if (n_tiles && solo) {
+            WalkFillArgs fa{};
+            fa.g = g; fa.keys = keys; fa.slot_of = C.slot_of; fa.pidx = pidx; fa.upoff = upoff; fa.ttot_slot = C.ttot_slot;
+            fa.pl_off = pl_off; fa.n_pl = n_pl; fa.n_real_pl = n_real_pl; fa.n_dl = n_dl; fa.n_tasks = n; fa.n_levels = n_levels;
+            fa.window = window; fa.window_usable = window - walk_groups * tile_slots;
+            fa.tab = C.tab; fa.tab_block = tab_block; fa.stream_off = C.stream_off; fa.stream = C.stream;
+            fa.lag_src = C.lag_src; fa.lag_counter = counters + 1;
+            w_fill_kernel<false><<<n_tiles, 512, 0, stream>>>(fa);
+        } else if (n_tiles) {
             FillArgs fa;
             fa.g = g; fa.keys = keys; fa.slot_of = C.slot_of; fa.pidx = pidx; fa.upoff = upoff; fa.ttot_slot = C.ttot_slot;
             fa.pl_off = pl_off; fa.n_pl = n_pl; fa.n_real_pl = n_real_pl; fa.n_dl = n_dl; fa.n_tasks = n; fa.n_groups = G;
@@ -1087,7 +1212,15 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         if (lag_filled != n_lag) throw std::runtime_error("compile_schedule: periodic snapshot count mismatch");
         unsigned int too_many = 0;
         cuda_ok(cudaMemcpy(&too_many, counters + 2, sizeof too_many, cudaMemcpyDeviceToHost), "copy");
+        if (too_many && solo) throw WalkUnsupported("walk form: a task has more than 62 upwind faces");
         if (too_many) throw std::runtime_error("compile_schedule: a task has more than 255 periodic upwind faces");
+        if (solo) {
+            unsigned int nf[2] = {0, 0};
+            cuda_ok(cudaMemcpy(nf, counters + 3, sizeof nf, cudaMemcpyDeviceToHost), "copy");
+            C.n_near = nf[0];
+            C.n_far = nf[1];
+            C.window = window;
+        }
         if (launch_counter) *launch_counter += 14;
         C.n_epilogue = m;
     } catch (...) {
@@ -1108,8 +1241,70 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
 }
 
 // One all-cells sweep over the compiled schedule.  Leaves the per-group sums in C.acc_cell / C.acc_per (s_rate_finish_kernel folds them).
+// One all-cells sweep in the walk form.  Leaves the incoming rates in C.inc_slot / C.acc_per (w_rate_finish_kernel folds them).
+inline void run_walk(Compiled &C, const double *att, const double *src, double n_dirs_total, double threshold,
+                     cudaStream_t stream, uint64_t *launch_counter) {
+    WalkArgs a;
+    a.stream = C.stream;
+    a.stream_off = C.stream_off;
+    a.tab = C.tab;
+    a.tab_off = C.tab_off;
+    a.out_slot = C.out_slot;
+    a.rec_slot = C.rec_slot;
+    a.acc_cell = C.acc_cell;
+    a.acc_per = C.acc_per;
+    a.n_cells = C.n_cells;
+    a.threshold = threshold;
+    a.stages = C.stages;
+    a.stage_bytes = C.stage_bytes;
+    a.window = C.window;
+    a.n_periodic = C.n_periodic;
+    a.l2_ahead = env_u32("SSW_WALK_L2_AHEAD", 0);   // measured: no gain (the copies are not DRAM-latency bound)
+    a.prof = nullptr;
+    unsigned long long *prof_dev = nullptr;
+    if (env_u32("SSW_STREAM_PROFILE", 0)) {
+        cuda_ok(cudaMalloc(&prof_dev, sizeof(unsigned long long) * 8 * (size_t)C.n_blocks), "malloc prof");
+        a.prof = prof_dev;
+    }
+    // every slot's incoming rate is stored exactly once per sweep; only the periodic rows have gaps
+    if (C.n_periodic)
+        cuda_ok(cudaMemsetAsync(C.acc_per, 0, sizeof(double) * (size_t)C.n_groups * C.n_periodic, stream), "memset acc_per");
+    w_rec_kernel<<<(unsigned)((C.n_tasks + 255) / 256), 256, 0, stream>>>(C.cell_of_slot, att, src, n_dirs_total, (uint32_t)C.n_tasks, C.rec_slot);
+    uint64_t launches = 2;
+    if (C.n_lag) {
+        s_lag_snapshot_kernel<<<(C.n_lag + 255) / 256, 256, 0, stream>>>(C.lag_src, C.n_lag, (uint32_t)C.n_tasks, C.out_slot);
+        ++launches;
+    }
+    WalkKernel kernel = walk_kernel_for(C.walk_groups, C.threads, prof_dev != nullptr);
+    const size_t smem = walk_smem_bytes(C.stages, C.stage_bytes, C.window);
+    cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem), "set max dynamic smem");
+    kernel<<<C.n_blocks, C.walk_groups * C.threads + 32 + 32 * kWalkGatherWarps, smem, stream>>>(a);
+    cuda_ok(cudaGetLastError(), "walk_kernel launch");
+    if (prof_dev) {
+        std::vector<unsigned long long> h(8 * (size_t)C.n_blocks);
+        cudaMemcpyAsync(h.data(), prof_dev, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, stream);
+        cudaStreamSynchronize(stream);
+        cudaFree(prof_dev);
+        double tot = 0, pkt = 0, tiles = 0, tmax = 0, loop = 0, outp = 0, bar = 0, gat = 0, dep = 0;
+        for (uint32_t b = 0; b < C.n_blocks; ++b) {
+            tot += (double)h[8 * b]; pkt += (double)h[8 * b + 1]; tiles += (double)h[8 * b + 2];
+            loop += (double)h[8 * b + 3]; outp += (double)h[8 * b + 4]; bar += (double)h[8 * b + 5]; gat += (double)h[8 * b + 6];
+            dep += (double)h[8 * b + 7];
+            tmax = std::max(tmax, (double)h[8 * b]);
+        }
+        fprintf(stderr, "[walk profile] blocks %u groups %u x %u threads tiles %.0f levels %u  cycles/block mean %.0f max %.0f  thread 0: packet wait %.1f%% "
+                        "level wait %.1f%% gather wait %.1f%% entries %.1f%% output %.1f%% barrier %.1f%%  cycles per tile %.0f  stage bytes %u stages %u window %u  near %.1f%% of %llu entries\n",
+                C.n_blocks, C.walk_groups, C.threads, tiles, C.n_levels, tot / C.n_blocks, tmax, 100.0 * pkt / tot, 100.0 * dep / tot, 100.0 * gat / tot, 100.0 * loop / tot, 100.0 * outp / tot,
+                100.0 * bar / tot, tot / tiles, C.stage_bytes, C.stages,
+                C.window, 100.0 * (double)C.n_near / (double)std::max<uint64_t>(1, C.n_near + C.n_far),
+                (unsigned long long)(C.n_near + C.n_far));
+    }
+    if (launch_counter) *launch_counter += launches;
+}
+
 inline void run_compiled(Compiled &C, const double2 *cellrec, double threshold, cudaStream_t stream,
                          uint64_t *launch_counter) {
+    if (C.solo) throw std::runtime_error("run_compiled: the walk form is run by run_walk");
     StreamArgs a;
     a.stream = C.stream;
     a.stream_off = C.stream_off;
@@ -1150,7 +1345,7 @@ inline void run_compiled(Compiled &C, const double2 *cellrec, double threshold, 
     }
     StreamKernel kernel = stream_kernel_for(C.threads, C.bps, prof_dev != nullptr, C.solo);
     const size_t smem = stream_smem_bytes(C.stages, C.stage_bytes);
-    cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "set max dynamic smem");
+    cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem), "set max dynamic smem");
     void *args[] = {&a};
     // cooperative launch only to guarantee co-residency of all blocks (the level barriers spin)
     cuda_ok(cudaLaunchCooperativeKernel((const void *)kernel, dim3(C.n_blocks), dim3(C.threads), args, smem, stream),
@@ -1166,6 +1361,12 @@ inline void run_compiled(Compiled &C, const double2 *cellrec, double threshold, 
             poll += (double)h[6 * b + 4]; rel += (double)h[6 * b + 5];
             tmax = std::max(tmax, (double)h[6 * b]);
         }
+        if (C.solo)
+            fprintf(stderr, "[solo profile] blocks %u tiles %.0f levels %u  cycles/block mean %.0f max %.0f  packet wait %.1f%%  phase 1 (gathers) %.1f%%  "
+                            "phase 2 (sums, stores) %.1f%%  cycles per tile %.0f  stage bytes %u stages %u\n",
+                    C.n_blocks, tiles, C.n_levels, tot / C.n_blocks, tmax, 100.0 * pkt / tot, 100.0 * bar / tot, 100.0 * rel / tot, tot / tiles,
+                    C.stage_bytes, C.stages);
+        else
         fprintf(stderr, "[stream profile] blocks %u tiles %.0f  cycles/block mean %.0f max %.0f  level change: arrive %.1f%% + wait behind it %.1f%% "
                         "(dependency poll %.1f%%)  packet wait %.1f%%  cycles per tile (excl. level changes) %.0f  pseudo-levels %u\n",
                 C.n_blocks, tiles, tot / C.n_blocks, tmax, 100.0 * rel / tot, 100.0 * bar / tot, 100.0 * poll / tot, 100.0 * pkt / tot,

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -21,6 +23,7 @@
 #include "kernels.cuh"
 #include "stream.cuh"
 #include "patch.cuh"
+#include "peer.cuh"
 
 namespace ssw {
 
@@ -55,14 +58,23 @@ template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    bool owned = true;
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
         p = nullptr;
         n = 0;
+        owned = true;
+    }
+    // a window into memory owned by somebody else (the per-cell arrays live in the rank's peer arena)
+    void view(void *ptr, size_t count) {
+        release();
+        p = static_cast<T *>(ptr);
+        n = count;
+        owned = false;
     }
     void alloc(size_t count) {
         release();
@@ -173,6 +185,19 @@ struct Sweep {
     void *collective_ctx = nullptr;
     DevBuf<double> chem_pack;                 // world_size x kPackFields x cells_per_rank
 
+    // direction sharding over peer-mapped memory (peer.cuh): the arena holds the per-cell state and the receive buffers
+    DevBuf<unsigned char> arena;
+    PeerTable pt{};
+    bool peers = false;            // the arenas of all ranks are attached: no hooks, no collective library
+    uint32_t peer_epoch = 0;
+    std::vector<void *> ipc_opened;
+    typedef int (*StreamWaitValue32)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+    StreamWaitValue32 stream_wait_value32 = nullptr;
+    int peer_wait_mode = 0;        // 0 stream memory operation, 1 host polling (ranks sharing a device), 2 polling kernel
+    cudaStream_t aux_stream = nullptr;
+    unsigned char *flags_host = nullptr;   // pinned
+    DevBuf<double> series_partial, series_sums, series_mass;   // ssw_time_series_compute
+
     // statistics / timers
     uint64_t stat[16] = {0};
     struct Pending { cudaEvent_t a, b; int cat; int lvl; };
@@ -182,9 +207,12 @@ struct Sweep {
     int coop_blocks_build = 0, coop_blocks_replay = 0, coop_blocks_mini = 0;
 
     ~Sweep() {
+        for (void *m : ipc_opened) cudaIpcCloseMemHandle(m);
         for (auto &p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
         for (auto e : event_pool) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
+        if (aux_stream) cudaStreamDestroy(aux_stream);
+        if (flags_host) cudaFreeHost(flags_host);
     }
 
     // ---- helpers ----
@@ -310,6 +338,15 @@ struct Sweep {
     void maybe_allreduce(double *buf, uint64_t n);
     uint32_t cells_per_rank() const { return (uint32_t)(((uint64_t)N + P.world_size - 1) / P.world_size); }
     void run_collective(int op, double *buf, uint64_t n_per_rank);
+    // peer-mapped exchange (peer.cuh)
+    void peer_attach(void *const *bases);
+    void peer_sync_point();
+    void peer_allreduce(double *buf, uint64_t n);
+    void peer_pull(uint64_t off);
+    PeerChem peer_chem() const;
+    PeerLevels peer_levels() const;
+    uint32_t own_first() const { return peers ? pt.first() : 0; }
+    uint32_t own_count() const { return peers ? pt.n_own() : N; }
 };
 
 static int coop_grid(const void *kernel, int threads, int num_sms) {
@@ -330,8 +367,8 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     if (p->n_levels < 1 || p->n_levels > 31)   // timestep_state.rs:72 asserts < 32
         fail(SSW_E_INVALID, "num_timestep_levels must be in [1, 31]");
     if (g->n_cells < 1 || g->n_cells > 0xfffffff0ull) fail(SSW_E_INVALID, "bad n_cells");
-    if (p->world_size < 0 || (p->world_size > 1 && (p->rank < 0 || p->rank >= p->world_size)))
-        fail(SSW_E_INVALID, "bad rank / world_size");
+    if (p->world_size < 0 || p->world_size > kMaxPeers || (p->world_size > 1 && (p->rank < 0 || p->rank >= p->world_size)))
+        fail(SSW_E_INVALID, "bad rank / world_size (at most %d ranks)", kMaxPeers);
     P = *p;
     if (P.world_size < 1) { P.world_size = 1; P.rank = 0; }
     D = p->n_dirs;
@@ -415,15 +452,26 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     face_off.alloc(N + 1); face_off.upload(off.data(), N + 1, stream);
     size.alloc(N); size.upload(g->cell_size, N, stream);
     volume.alloc(N); volume.upload(g->cell_volume, N, stream);
+    // per-cell state: one arena per rank, so that the ranks of a sharded job can map each other's (peer.cuh)
+    {
+        const PeerLayout L = peer_layout(N, P.world_size);
+        arena.alloc(L.bytes);
+        arena.zero(stream);
+        pt.L = L;
+        pt.world = P.world_size;
+        pt.rank = P.rank;
+        pt.n_per = cells_per_rank();
+        pt.n_cells = N;
+        for (int r = 0; r < kMaxPeers; ++r) pt.base[r] = nullptr;
+        pt.base[P.rank] = arena.p;
+        x.view(arena.p + L.x, N); T.view(arena.p + L.T, N); ts.view(arena.p + L.ts, N); tau.view(arena.p + L.tau, N);
+        prev_rate.view(arena.p + L.prev, N); att.view(arena.p + L.att, N); ion_time.view(arena.p + L.ion, N);
+        photon.view(arena.p + L.photon, N); level.view(arena.p + L.level, N);
+    }
     rho.alloc(N); rho.upload(density, N, stream);
-    x.alloc(N); x.upload(xhii, N, stream);
-    T.alloc(N); T.upload(temperature, N, stream);
+    x.upload(xhii, N, stream);
+    T.upload(temperature, N, stream);
     src.alloc(N); src.upload(source, N, stream);
-    ts.alloc(N); ts.zero(stream);
-    tau.alloc(N); tau.zero(stream);
-    prev_rate.alloc(N); prev_rate.zero(stream);
-    att.alloc(N);
-    ion_time.alloc(N);
     {
         std::vector<double> infv(N, std::numeric_limits<double>::infinity());   // IonizationTime::default(), components.rs:79-83
         ion_time.upload(infv.data(), N, stream);
@@ -431,7 +479,6 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     }
     pidx.alloc(N); pidx.upload(pidx_h.data(), N, stream);
     pcells.alloc(n_periodic); if (n_periodic) pcells.upload(pcells_h.data(), n_periodic, stream);
-    level.alloc(N);
     CUDA_CHECK(cudaMemsetAsync(level.p, P.n_levels - 1, N, stream));  // initial_level, mod.rs:206
     const size_t ND = (size_t)N * Dl;
     q.alloc(ND); q.zero(stream);
@@ -446,7 +493,6 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     cellrec.alloc(N);
     cell_tmp.alloc(N);
     cell_tmp2.alloc(N);
-    photon.alloc(N); photon.zero(stream);
     hist.alloc(33);
     chem_stats.alloc(1); chem_stats.zero(stream);
     CUDA_CHECK(cudaStreamSynchronize(stream));  // host vectors go out of scope
@@ -690,8 +736,125 @@ void Sweep::build_mini(Schedule &S) {
     S.mini_slot_state = state != nullptr;
 }
 
+// ------------------------------------------------------------------------------------------
+// direction sharding over peer-mapped memory (peer.cuh)
+// ------------------------------------------------------------------------------------------
+void Sweep::peer_attach(void *const *bases) {
+    if (P.world_size <= 1) fail(SSW_E_INVALID, "peer attach needs world_size > 1");
+    for (int r = 0; r < P.world_size; ++r) {
+        if (r == P.rank) continue;
+        if (!bases[r]) fail(SSW_E_INVALID, "no arena for rank %d", r);
+        pt.base[r] = static_cast<unsigned char *>(bases[r]);
+    }
+    // The wait half of a synchronisation point.  One rank per device (production): a stream memory operation
+    // (cuStreamWaitValue32) -- nothing of the host or of an SM is involved; a polling kernel where the driver has none.
+    // Ranks that SHARE a device (tests): the host polls the flag words instead, because a stream blocked on a peer
+    // would dead-lock with the implicit device-wide synchronisation of cudaFree / cudaMalloc on the peer's thread.
+    // SSW_PEER_WAIT = 0 / 1 / 2 overrides.
+    stream_wait_value32 = nullptr;
+    peer_wait_mode = (int)stream_env_u32("SSW_PEER_WAIT", (P.flags & SSW_FLAG_SHARED_DEVICE) ? 1 : 0);
+    if (peer_wait_mode == 0) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess && fn) {
+            stream_wait_value32 = reinterpret_cast<StreamWaitValue32>(fn);
+        } else {
+            (void)cudaGetLastError();
+            peer_wait_mode = 2;
+        }
+    }
+    if (peer_wait_mode == 1 && !aux_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+    peers = true;
+}
+
+// every rank signals every rank, then waits for everybody's signal: what this rank queued before the point is visible
+// to all ranks behind it, and vice versa
+void Sweep::peer_sync_point() {
+    const size_t t = tic(T_ALLREDUCE);
+    ++peer_epoch;
+    peer_signal_kernel<<<1, 32, 0, stream>>>(pt, peer_epoch);
+    launched();
+    if (peer_wait_mode == 0) {
+        for (int r = 0; r < P.world_size; ++r) {
+            const unsigned long long addr = (unsigned long long)(uintptr_t)(arena.p + pt.L.flags + (uint64_t)r * kPeerFlagStride);
+            const int rc = stream_wait_value32(stream, addr, peer_epoch, /*CU_STREAM_WAIT_VALUE_GEQ*/ 0u);
+            if (rc != 0) fail(SSW_E_COMM, "cuStreamWaitValue32 failed (%d)", rc);
+        }
+    } else if (peer_wait_mode == 1) {
+        const auto t00 = std::chrono::steady_clock::now();
+        CUDA_CHECK(cudaStreamSynchronize(stream));   // my signal is out
+        if (!flags_host) CUDA_CHECK(cudaHostAlloc((void **)&flags_host, (size_t)kMaxPeers * kPeerFlagStride, cudaHostAllocDefault));
+        unsigned char *flags_h = flags_host;
+        const size_t flags_bytes = (size_t)P.world_size * kPeerFlagStride;
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned long polls = 0;
+        for (;;) {
+            ++polls;
+            CUDA_CHECK(cudaMemcpyAsync(flags_h, arena.p + pt.L.flags, flags_bytes, cudaMemcpyDeviceToHost, aux_stream));
+            CUDA_CHECK(cudaStreamSynchronize(aux_stream));
+            bool ok = true;
+            for (int r = 0; r < P.world_size && ok; ++r) {
+                uint32_t v;
+                std::memcpy(&v, flags_h + (size_t)r * kPeerFlagStride, sizeof v);
+                ok = (int32_t)(v - peer_epoch) >= 0;
+            }
+            if (ok) break;
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60))
+                fail(SSW_E_COMM, "peer exchange: a rank did not reach synchronisation point %u within 60 s", peer_epoch);
+            std::this_thread::yield();
+        }
+        if (stream_env_u32("SSW_PEER_DEBUG", 0)) {
+            const auto t1 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[peer %d] point %u: stream sync %.3f ms, flag wait %.3f ms (%lu polls)\n", P.rank, peer_epoch,
+                    std::chrono::duration<double, std::milli>(t0 - t00).count(), std::chrono::duration<double, std::milli>(t1 - t0).count(), polls);
+        }
+    } else {
+        peer_wait_kernel<<<1, 32, 0, stream>>>(pt, peer_epoch);
+        launched();
+    }
+    CUDA_CHECK(cudaGetLastError());
+    toc(t);
+}
+
+// in-place sum over the ranks, folded in rank order on every rank (deterministic): each rank exposes its buffer in
+// its arena, everybody reads everybody's
+void Sweep::peer_allreduce(double *buf, uint64_t n) {
+    if (n > N) fail(SSW_E_INVALID, "peer all-reduce of more than n_cells values");
+    CUDA_CHECK(cudaMemcpyAsync(arena.p + pt.L.scratch, buf, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+    peer_sync_point();
+    peer_sum_kernel<<<cdiv(n, 256), 256, 0, stream>>>(pt, pt.L.scratch, buf, n);
+    launched();
+    peer_sync_point();   // nobody overwrites its scratch before everybody has read it
+}
+
+void Sweep::peer_pull(uint64_t off) {
+    peer_pull_kernel<<<cdiv(N, 256), 256, 0, stream>>>(pt, off);
+    launched();
+}
+
+PeerChem Sweep::peer_chem() const {
+    PeerChem pc{};
+    pc.world = peers ? P.world_size : 0;
+    if (!peers) return pc;
+    pc.first = pt.first();
+    pc.n_own = pt.n_own();
+    pc.n_per = pt.n_per;
+    pc.recv = pt.f64(P.rank, pt.L.recv);
+    for (int r = 0; r < P.world_size; ++r) pc.att[r] = pt.f64(r, pt.L.att);
+    return pc;
+}
+
+PeerLevels Sweep::peer_levels() const {
+    PeerLevels pl{};
+    pl.world = peers ? P.world_size : 0;
+    for (int r = 0; peers && r < P.world_size; ++r) pl.level[r] = pt.base[r] + pt.L.level;
+    return pl;
+}
+
 void Sweep::maybe_allreduce(double *buf, uint64_t n) {
     if (P.world_size <= 1) return;  // one direction shard: no collective (north_star)
+    if (peers) return peer_allreduce(buf, n);
     if (!allreduce) fail(SSW_E_COMM, "world_size > 1 but no all-reduce hook set (ssw_set_allreduce)");
     const size_t t = tic(T_ALLREDUCE);
     // stream-ordered: the hook enqueues the collective behind the work already queued on `stream`
@@ -790,10 +953,34 @@ void Sweep::single_sweep(int cur) {
                         patch_note = e.what();   // keep the level-barrier stream
                     }
                 }
-                if (!patched)
-                    compile_schedule(S.compiled, grid_view(), S.tasks.p, S.level_off.p, S.n_tasks, S.n_levels, Dl,
-                                     pcells.p, n_periodic, pidx.p, q.p, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES],
-                                     /*solo_default=*/true);
+                if (!patched) {
+                    // the walk form (one block per direction, recent rates in a shared-memory window, walk.cuh) unless
+                    // the grid does not fit it; then the level-barrier stream
+                    // Which one: the stream form crosses one device-wide barrier per wavefront level (~4.5 us each,
+                    // profiles/), the walk form crosses none but keeps one direction on one SM.  Walk when the barriers
+                    // would dominate the stream form's byte time (unstructured grids: thousands of levels) and there
+                    // are enough directions to occupy the SMs; SSW_WALK = 0 / 1 decides by hand.
+                    const double barrier_s = 4.5e-6 * (double)S.n_levels;
+                    const double stream_s = 12.0 * 0.5 * (double)F * (double)Dl / 2.5e12;
+                    bool want_walk = Dl >= 32 && barrier_s > stream_s;
+                    const uint32_t forced = stream_env_u32("SSW_WALK", 2);
+                    if (forced < 2) want_walk = forced != 0;
+                    bool walked = false;
+                    try {
+                        if (want_walk) {
+                            compile_schedule(S.compiled, grid_view(), S.tasks.p, S.level_off.p, S.n_tasks, S.n_levels, Dl,
+                                             pcells.p, n_periodic, pidx.p, q.p, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES],
+                                             /*allow_walk=*/true);
+                            walked = true;
+                        }
+                    } catch (const WalkUnsupported &e) {
+                        patch_note += std::string(patch_note.empty() ? "" : "; ") + e.what();
+                    }
+                    if (!walked)
+                        compile_schedule(S.compiled, grid_view(), S.tasks.p, S.level_off.p, S.n_tasks, S.n_levels, Dl,
+                                         pcells.p, n_periodic, pidx.p, q.p, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES],
+                                         /*allow_walk=*/false);
+                }
             } catch (const std::exception &e) {
                 fail(SSW_E_CUDA, "%s", e.what());
             }
@@ -805,6 +992,10 @@ void Sweep::single_sweep(int cur) {
         SweepArgs a = sweep_args(cur);
         if (use_compiled && S.compiled.valid) {
             try {
+                if (S.compiled.solo) {
+                    run_walk(S.compiled, att.p, src.p, (double)D, P.significant_rate_threshold_per_s, stream,
+                             &stat[SSW_STAT_KERNEL_LAUNCHES]);
+                } else {
                 cellrec_kernel<<<cdiv(N, 256), 256, 0, stream>>>(att.p, src.p, (double)D, N, cellrec.p);
                 launched();
                 if (S.compiled.patch_mode)
@@ -813,6 +1004,7 @@ void Sweep::single_sweep(int cur) {
                 else
                     run_compiled(S.compiled, cellrec.p, P.significant_rate_threshold_per_s, stream,
                                  &stat[SSW_STAT_KERNEL_LAUNCHES]);
+                }
             } catch (const std::exception &e) {
                 fail(SSW_E_CUDA, "%s", e.what());
             }
@@ -885,7 +1077,20 @@ void Sweep::single_sweep(int cur) {
     cp.scale_factor = P.scale_factor;
     cp.safety = P.chemistry_timestep_safety_factor;
     cp.prevent_cooling = P.prevent_cooling;
-    if (all && P.world_size > 1 && collective) {
+    if (P.world_size > 1 && peers) {
+        // peer-mapped exchange: partial rates straight into the owners' receive buffers, chemistry on the owner, new
+        // absorption factors straight into every rank's array (peer.cuh)
+        peer_push_rates_kernel<<<cdiv(n_act, 256), 256, 0, stream>>>(pt, act, n_act, rate_act.p);
+        launched();
+        peer_sync_point();
+        const uint32_t n_launch = all ? pt.n_own() : n_act;
+        if (n_launch) {
+            chemistry_kernel<<<cdiv(n_launch, 128), 128, 0, stream>>>(cell_view(), act, n_launch, nullptr, cp, chem_stats.p,
+                                                                       all ? pt.first() : 0u, peer_chem());
+            launched();
+        }
+        peer_sync_point();
+    } else if (all && P.world_size > 1 && collective) {
         // all cells active on W ranks: reduce-scatter the partial rates, update the own slice of cells, all-gather
         // the results -- the chemistry is not replicated W times, and every rank ends with bit-identical state
         const uint32_t n_per = cells_per_rank();
@@ -895,7 +1100,7 @@ void Sweep::single_sweep(int cur) {
         run_collective(SSW_COLL_REDUCE_SCATTER, rate_act.p, n_per);
         double *chunk = chem_pack.p + (size_t)P.rank * kPackFields * n_per;
         if (n_own) {
-            chemistry_kernel<<<cdiv(n_own, 128), 128, 0, stream>>>(cell_view(), nullptr, n_own, rate_act.p + first, cp, chem_stats.p, first);
+            chemistry_kernel<<<cdiv(n_own, 128), 128, 0, stream>>>(cell_view(), nullptr, n_own, rate_act.p + first, cp, chem_stats.p, first, PeerChem{});
             chem_pack_kernel<<<cdiv(n_own, 256), 256, 0, stream>>>(cell_view(), first, n_own, n_per, chunk);
             launched(2);
         }
@@ -904,7 +1109,7 @@ void Sweep::single_sweep(int cur) {
         launched();
     } else {
         maybe_allreduce(rate_act.p, n_act);
-        chemistry_kernel<<<cdiv(n_act, 128), 128, 0, stream>>>(cell_view(), act, n_act, rate_act.p, cp, chem_stats.p, 0u);
+        chemistry_kernel<<<cdiv(n_act, 128), 128, 0, stream>>>(cell_view(), act, n_act, rate_act.p, cp, chem_stats.p, 0u, PeerChem{});
         launched();
     }
     CUDA_CHECK(cudaGetLastError());
@@ -916,13 +1121,31 @@ void Sweep::single_sweep(int cur) {
 void Sweep::update_timestep_levels() {
     const size_t t = tic(T_LEVELS);
     hist.zero(stream);
-    levels_kernel<<<cdiv(N, 256), 256, 0, stream>>>(tau.p, level.p, N, P.n_levels, P.max_timestep_s,
-                                                    P.timestep_safety_factor, lowest_allowed, hist.p);
+    const uint32_t first = own_first(), n_own = own_count();
+    if (n_own)
+        levels_kernel<<<cdiv(n_own, 256), 256, 0, stream>>>(tau.p, level.p, first, n_own, P.n_levels, P.max_timestep_s,
+                                                            P.timestep_safety_factor, lowest_allowed, hist.p, peer_levels());
     launched();
     unsigned long long h[33];
+    if (peers) {
+        // the owners pushed the new levels into every rank's array; the per-level counts travel the same way
+        peer_hist_push_kernel<<<1, 64, 0, stream>>>(pt, hist.p);
+        launched();
+        peer_sync_point();
+        std::vector<unsigned long long> all_h((size_t)P.world_size * kPeerHistWords);
+        CUDA_CHECK(cudaMemcpyAsync(all_h.data(), arena.p + pt.L.hist, sizeof(unsigned long long) * all_h.size(),
+                                   cudaMemcpyDeviceToHost, stream));
+        toc(t);
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        for (int i = 0; i < 33; ++i) {
+            h[i] = 0;
+            for (int r = 0; r < P.world_size; ++r) h[i] += all_h[(size_t)r * kPeerHistWords + i];
+        }
+    } else {
     CUDA_CHECK(cudaMemcpyAsync(h, hist.p, sizeof h, cudaMemcpyDeviceToHost, stream));
     toc(t);
     CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
     for (int l = 0; l < P.n_levels; ++l) bin_count[l] = h[l];
     // level sets are rebuilt only when the active sets changed (north_star)
     if (h[32] != 0) levels_version++;
@@ -941,10 +1164,12 @@ double Sweep::run_sweeps() {
     const double elapsed = P.max_timestep_s * std::ldexp(1.0, -lowest_allowed);  // timestep_state.rs:77-79
     if (first_done && lowest_allowed > 0) lowest_allowed -= 1;                   // :37-48
     first_done = true;
-    update_timestep_levels();
     sim_time += elapsed;
-    ionization_time_kernel<<<cdiv(N, 256), 256, 0, stream>>>(x.p, ion_time.p, N, sim_time);
-    launched();
+    if (own_count()) {   // before the level update: its synchronisation point also publishes the ionization times
+        ionization_time_kernel<<<cdiv(own_count(), 256), 256, 0, stream>>>(x.p, ion_time.p, own_first(), own_count(), sim_time);
+        launched();
+    }
+    update_timestep_levels();
     // fold the chemistry statistics
     ChemStats cs;
     CUDA_CHECK(cudaMemcpyAsync(&cs, chem_stats.p, sizeof cs, cudaMemcpyDeviceToHost, stream));
@@ -971,16 +1196,31 @@ void Sweep::all_rates(double *dev_out) {
 void Sweep::read_field(int field, double *out, bool wait) {
     bind();
     const double *srcp = nullptr;
+    // peer-mapped sharding: the chemistry state of a cell lives on its owner; the reading rank fetches the other
+    // owners' slices (they are final once its own ssw_run_sweeps has returned, peer.cuh)
+    auto owned = [&](const DevBuf<double> &buf, uint64_t off) {
+        if (peers && out) peer_pull(off);
+        return (const double *)buf.p;
+    };
     switch (field) {
-    case SSW_F_XHII: srcp = x.p; break;
-    case SSW_F_TEMPERATURE: srcp = T.p; break;
-    case SSW_F_TIMESTEP: srcp = ts.p; break;
-    case SSW_F_CHANGE_TIMESCALE: srcp = tau.p; break;
-    case SSW_F_PREVIOUS_RATE: srcp = prev_rate.p; break;
+    case SSW_F_XHII: srcp = owned(x, pt.L.x); break;
+    case SSW_F_TEMPERATURE: srcp = owned(T, pt.L.T); break;
+    case SSW_F_TIMESTEP: srcp = owned(ts, pt.L.ts); break;
+    case SSW_F_CHANGE_TIMESCALE: srcp = owned(tau, pt.L.tau); break;
+    case SSW_F_PREVIOUS_RATE: srcp = owned(prev_rate, pt.L.prev); break;
     case SSW_F_DENSITY: srcp = rho.p; break;
     case SSW_F_SOURCE: srcp = src.p; break;
-    case SSW_F_IONIZATION_TIME: srcp = ion_time.p; break;
+    case SSW_F_IONIZATION_TIME: srcp = owned(ion_time, pt.L.ion); break;
     case SSW_F_PHOTON_RATE:
+        if (photon_valid && peers) {
+            // every rank keeps the sum over ITS directions current in its arena: fold them in rank order
+            peer_sync_point();
+            peer_sum_kernel<<<cdiv(N, 256), 256, 0, stream>>>(pt, pt.L.photon, cell_tmp.p, N);
+            launched();
+            peer_sync_point();
+            srcp = cell_tmp.p;
+            break;
+        }
         if (photon_valid) {
             // kept current by the sweeps themselves: the all-cells sweep leaves sum_d incoming in its
             // accumulators, partial sweeps patch the cells they touch
@@ -1002,6 +1242,7 @@ void Sweep::read_field(int field, double *out, bool wait) {
     case SSW_F_HEATING_RATE:
     case SSW_F_RECOMBINATION_RATE:
     case SSW_F_COLLISIONAL_IONIZATION_RATE:
+        if (peers) { peer_pull(pt.L.x); peer_pull(pt.L.T); }   // the outputs are evaluated for all cells on every rank
         all_rates(rate_act.p);
         chem_output_kernel<<<cdiv(N, 256), 256, 0, stream>>>(cell_view(), N, rate_act.p, P.scale_factor, field, cell_tmp.p);
         launched();
@@ -1093,6 +1334,67 @@ int ssw_set_collectives(ssw_handle *h, ssw_collective_fn fn, void *ctx) {
     SSW_CATCH
 }
 
+int ssw_peer_arena(ssw_handle *h, void **base, uint64_t *bytes) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    if (base) *base = h->s.arena.p;
+    if (bytes) *bytes = h->s.pt.L.bytes;
+    SSW_CATCH
+}
+
+int ssw_peer_export(ssw_handle *h, void *ipc_handle_out) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    if (!ipc_handle_out) ssw::fail(SSW_E_INVALID, "null out pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SSW_PEER_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    CUDA_CHECK(cudaSetDevice(h->s.device));
+    cudaIpcMemHandle_t m;
+    CUDA_CHECK(cudaIpcGetMemHandle(&m, h->s.arena.p));
+    std::memcpy(ipc_handle_out, &m, sizeof m);
+    SSW_CATCH
+}
+
+int ssw_peer_attach_ipc(ssw_handle *h, const void *ipc_handles) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    auto &s = h->s;
+    if (!ipc_handles) ssw::fail(SSW_E_INVALID, "null handles");
+    CUDA_CHECK(cudaSetDevice(s.device));
+    std::vector<void *> bases(s.P.world_size, nullptr);
+    for (int r = 0; r < s.P.world_size; ++r) {
+        if (r == s.P.rank) { bases[r] = s.arena.p; continue; }
+        cudaIpcMemHandle_t m;
+        std::memcpy(&m, static_cast<const unsigned char *>(ipc_handles) + (size_t)r * SSW_PEER_HANDLE_BYTES, sizeof m);
+        void *ptr = nullptr;
+        CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, m, cudaIpcMemLazyEnablePeerAccess));
+        s.ipc_opened.push_back(ptr);
+        bases[r] = ptr;
+    }
+    s.peer_attach(bases.data());
+    SSW_CATCH
+}
+
+int ssw_peer_attach(ssw_handle *h, void *const *arena_bases) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    auto &s = h->s;
+    if (!arena_bases) ssw::fail(SSW_E_INVALID, "null bases");
+    CUDA_CHECK(cudaSetDevice(s.device));
+    // handles of one process on different devices: map the peers' memory
+    for (int r = 0; r < s.P.world_size; ++r) {
+        if (r == s.P.rank || !arena_bases[r]) continue;
+        cudaPointerAttributes a;
+        CUDA_CHECK(cudaPointerGetAttributes(&a, arena_bases[r]));
+        if (a.device != s.device) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(e);
+            (void)cudaGetLastError();
+        }
+    }
+    s.peer_attach(arena_bases);
+    SSW_CATCH
+}
+
 int ssw_run_sweeps(ssw_handle *h, double *time_elapsed_s) {
     SSW_TRY
     REQUIRE_HANDLE(h);
@@ -1109,8 +1411,10 @@ int ssw_set_inputs(ssw_handle *h, const double *density, const double *source) {
     if (density) s.rho.upload(density, s.N, s.stream);
     if (source) s.src.upload(source, s.N, s.stream);
     if (density) {
+        // the absorption factor needs x: on the owner only under peer-mapped sharding, which then tells the others
+        if (s.peers) ssw::peer_pull_kernel<<<ssw::cdiv(s.N, 256), 256, 0, s.stream>>>(s.pt, s.pt.L.x);
         ssw::attenuation_kernel<<<ssw::cdiv(s.N, 256), 256, 0, s.stream>>>(s.cell_view(), s.N);
-        s.launched();
+        s.launched(2);
     }
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
     SSW_CATCH
@@ -1148,10 +1452,13 @@ int ssw_time_series_compute(ssw_handle *h, const double *mass, int32_t with_rate
     auto &s = h->s;
     s.bind();
     const uint32_t nb = ssw::cdiv(s.N, 256);
-    ssw::DevBuf<double> partial, sums, mass_dev;
-    partial.alloc((size_t)nb * ssw::kSeriesSums);
-    sums.alloc(ssw::kSeriesSums);
-    if (mass) { mass_dev.alloc(s.N); mass_dev.upload(mass, s.N, s.stream); }
+    auto &partial = s.series_partial;
+    auto &sums = s.series_sums;
+    auto &mass_dev = s.series_mass;
+    partial.ensure((size_t)nb * ssw::kSeriesSums);   // allocated once, on the first call
+    sums.ensure(ssw::kSeriesSums);
+    if (mass) { mass_dev.ensure(s.N); mass_dev.upload(mass, s.N, s.stream); }
+    if (s.peers) { s.peer_pull(s.pt.L.x); s.peer_pull(s.pt.L.T); }
     const double *gamma = nullptr;
     if (with_rates) {   // PhotoionizationRate of every cell, as sweep_optional_output_system computes it
         s.all_rates(s.rate_act.p);

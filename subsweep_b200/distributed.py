@@ -79,6 +79,19 @@ def make_collectives(device, group=None):
     return collective
 
 
+def attach_peers(sweep, group=None) -> None:
+    """Peer-mapped direction sharding (one process per GPU of one box): exchange the ranks' 64-byte CUDA IPC handles
+    with ``torch.distributed`` -- the only thing the process group is used for -- and attach them.  From then on the
+    library moves rate partials, absorption factors and timestep levels itself over NVLink (csrc/peer.cuh)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    handles = [None] * world
+    dist.all_gather_object(handles, sweep.peer_export(), group=group)
+    sweep.peer_attach_ipc(handles)
+    dist.barrier(group=group)
+
+
 def init_from_env(backend: str | None = None):
     """Initialise torch.distributed from torchrun's environment; returns (rank, world, local_rank)."""
     import torch

@@ -195,9 +195,8 @@ class Sweep:
             if pos.shape != (N, 3):
                 raise ValueError("positions must have shape (n_cells, 3)")
             self._check(self.lib.ssw_set_cell_positions(self._h, capi.dptr(pos)))
-        if world_size > 1:
-            if allreduce is None:
-                raise ValueError("world_size > 1 needs an allreduce callable")
+        # world_size > 1: either attach the peers' arenas (peer_attach / peer_attach_ipc, the NVLink path) or give hooks
+        if world_size > 1 and allreduce is not None:
             self.set_allreduce(allreduce)
             if collectives is not None:
                 self.set_collectives(collectives)
@@ -215,6 +214,31 @@ class Sweep:
         """Reduce-scatter / all-gather hook (ssw_set_collectives): chemistry sliced by cells instead of replicated."""
         self._coll_cb = collective_trampoline(fn)
         self._check(self.lib.ssw_set_collectives(self._h, self._coll_cb, None))
+
+    # -- peer-mapped direction sharding (include/subsweep_b200.h, "direction sharding without hooks") -------------
+    def peer_arena(self) -> tuple[int, int]:
+        """(device pointer, bytes) of this rank's arena."""
+        base, nbytes = C.c_void_p(), C.c_uint64()
+        self._check(self.lib.ssw_peer_arena(self._h, C.byref(base), C.byref(nbytes)))
+        return int(base.value), int(nbytes.value)
+
+    def peer_export(self) -> bytes:
+        """The arena's CUDA IPC handle (64 bytes) for the other processes of the box."""
+        buf = C.create_string_buffer(capi.PEER_HANDLE_BYTES)
+        self._check(self.lib.ssw_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_attach_ipc(self, handles: Sequence[bytes]) -> None:
+        """Attach the arenas of all ranks from their IPC handles (rank order; the own entry is ignored)."""
+        blob = b"".join(handles)
+        if len(blob) != capi.PEER_HANDLE_BYTES * self.world_size:
+            raise ValueError("need one 64-byte handle per rank")
+        self._check(self.lib.ssw_peer_attach_ipc(self._h, C.c_char_p(blob)))
+
+    def peer_attach(self, bases: Sequence[int]) -> None:
+        """Attach the arenas of all ranks by device pointer (handles of one process)."""
+        arr = (C.c_void_p * self.world_size)(*[C.c_void_p(b) for b in bases])
+        self._check(self.lib.ssw_peer_attach(self._h, arr))
 
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value:

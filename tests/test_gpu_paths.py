@@ -74,3 +74,30 @@ def test_queued_read_back_equals_blocking_read(cuda_lib):
     s.sync()
     for k in names:
         assert np.array_equal(queued[k], s.read(k), equal_nan=True), k
+
+
+@pytest.mark.parametrize("kind,n,periodic,n_dirs", [("voronoi", 10, True, 84), ("voronoi", 10, False, 32), ("cartesian", 12, True, 84),
+                                                    ("jittered", 9, True, 64)])
+def test_walk_form_matches_stream_form(cuda_lib, monkeypatch, kind, n, periodic, n_dirs):
+    """The two compiled forms of the all-cells sweep on grids without a patch form: one block per direction walking its
+    wavefront with the recent rates in a shared-memory window (walk.cuh, SSW_WALK=1) against the level-barrier stream
+    (stream.cuh, SSW_WALK=0).  Per task the arithmetic is the same: outgoing rates bit-identical; the per-cell rate is
+    folded over directions in a different order (round-off)."""
+    params, g, f = make_problem(kind, n, periodic, n_dirs=n_dirs, n_levels=3, max_timestep_myr=0.25)
+    res = {}
+    for form in ("0", "1"):
+        monkeypatch.setenv("SSW_WALK", form)
+        s = Sweep(params, g, **f, flags=capi.FLAG_NO_PATCH_PATH)
+        s.run_sweeps()
+        res[form, "first"] = s.dir_state("outgoing")
+        for _ in range(5):
+            s.run_sweeps()
+        res[form] = {k: s.read(k) for k in ("ionized_hydrogen_fraction", "temperature", "change_timescale", "photon_rate")}
+        res[form]["levels"] = s.levels()
+        res[form]["outgoing"] = s.dir_state("outgoing")
+        s.close()
+    assert np.array_equal(res["0", "first"], res["1", "first"])          # same inputs: bit-identical outgoing rates
+    assert np.array_equal(res["0"]["levels"], res["1"]["levels"])
+    for k, v in res["0"].items():
+        if k != "levels":
+            assert_close(res["1"][k], v, 1e-11, floor=1e-7 * np.nanmax(np.abs(v)), what=k)

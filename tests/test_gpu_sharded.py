@@ -112,6 +112,76 @@ def run_sharded(params, g, f, world, steps, sliced):
     return out
 
 
+def run_peers(params, g, f, world, steps):
+    """W ranks as W host threads, one handle each on the same device, exchanging through peer-mapped arenas
+    (ssw_peer_arena / ssw_peer_attach): no hooks, the threads run concurrently and meet only on the device."""
+    barrier = threading.Barrier(world, timeout=120)
+    create = threading.Lock()
+    sweeps, out, errors = [None] * world, [None] * world, []
+
+    def work(rank):
+        try:
+            with create:
+                sweeps[rank] = Sweep(params, g, **f, rank=rank, world_size=world, flags=capi.FLAG_SHARED_DEVICE)
+            barrier.wait()
+            s = sweeps[rank]
+            s.peer_attach([sw.peer_arena()[0] for sw in sweeps])
+            barrier.wait()
+            for _ in range(steps):
+                s.run_sweeps()
+            res = {k: s.read(k) for k in FIELDS}          # photon_rate is a collective: same order on every rank
+            res["levels"] = s.levels()
+            res["outgoing"] = s.dir_state("outgoing")
+            res["macro_tiles"] = s.stat("patch_macro_tiles")
+            res["chem_cells"] = s.stat("chem_cells")
+            res["series"] = s.time_series()
+            barrier.wait()
+            s.close()
+            out[rank] = res
+        except Exception as exc:   # noqa: BLE001
+            errors.append(exc)
+            barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("kind,n,periodic", [("cartesian", 12, True), ("voronoi", 8, False), ("voronoi", 8, True)])
+def test_peer_mapped_shards_reproduce_the_single_rank_result(cuda_lib, monkeypatch, kind, n, periodic, world):
+    """The NVLink path of direction sharding (csrc/peer.cuh): rate partials pushed into the owners' receive buffers,
+    chemistry on the owner, absorption factors and timestep levels pushed to every rank."""
+    monkeypatch.setenv("SSW_PATCH_CELLS", "64")
+    params, g, f = make_problem(kind, n, periodic, n_dirs=21, n_levels=3, max_timestep_myr=0.25)
+    steps = 5
+    one = Sweep(params, g, **f)
+    for _ in range(steps):
+        one.run_sweeps()
+    ranks = run_peers(params, g, f, world, steps)
+    for r in ranks[1:]:   # every rank assembles the same cell state, bit for bit
+        for k in FIELDS + ("levels",):
+            assert np.array_equal(r[k], ranks[0][k], equal_nan=True), k
+    assert np.array_equal(ranks[0]["levels"], one.levels())
+    for k in FIELDS:
+        b = one.read(k)
+        floor = 1e-7 * np.nanmax(np.abs(b)) if k in ("previous_rate", "photon_rate") else 0.0
+        assert_close(ranks[0][k], b, 1e-9, floor=floor, what=k)
+    out = np.concatenate([r["outgoing"] for r in ranks], axis=1)
+    b = one.dir_state("outgoing")
+    assert_close(out, b, 1e-9, floor=1e-7 * max(np.abs(b).max(), 1e-300), what="outgoing")
+    assert sum(r["chem_cells"] for r in ranks) == one.stat("chem_cells")     # every cell update ran on exactly one rank
+    ts = one.time_series()
+    for key, v in ranks[-1]["series"].items():
+        if np.isfinite(ts[key]):
+            assert abs(v - ts[key]) <= 1e-9 * abs(ts[key]), key
+
+
 @pytest.mark.parametrize("world,sliced", [(2, False), (2, True), (3, True)])
 @pytest.mark.parametrize("kind,n,periodic", [("cartesian", 12, True), ("voronoi", 8, False)])
 def test_direction_shards_reproduce_the_single_rank_result(cuda_lib, monkeypatch, kind, n, periodic, world, sliced):
