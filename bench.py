@@ -270,7 +270,7 @@ def workload_config(args, note: str | None = None) -> dict:
     cfg = {
         "workload": text,
         "cells": args.n ** 3, "directions": args.dirs, "timestep_levels": args.levels, "grid": args.grid,
-        "parallelism": f"direction sharding x{args.gpus}" if args.gpus > 1 else "single GPU",
+        "parallelism": (f"direction sharding x{args.gpus}, peer-mapped exchange over NVLink" if args.gpus > 1 else "single GPU"),
         "l2": "working set (per-direction flux state + level sets, > 2 GB) is far larger than the 126 MB L2; no flush needed",
         "step": "one Sweep::run_sweeps call (all single sweeps of the level order + chemistry + level update)",
     }
@@ -291,7 +291,7 @@ def run_b200(args) -> None:
     import torch
     import torch.distributed as dist
     from subsweep_b200 import Sweep, build as libbuild
-    from subsweep_b200.distributed import init_from_env, make_allreduce, make_collectives
+    from subsweep_b200.distributed import attach_peers, init_from_env, make_allreduce, make_collectives
 
     rank, world, local_rank = init_from_env()
     if world != args.gpus and world > 1:
@@ -306,8 +306,11 @@ def run_b200(args) -> None:
         dist.barrier()
 
     params, g, fields = build_workload(args.n, args.grid, args.dirs, args.levels, args.workload, args.front_scale)
-    allreduce = make_allreduce(device) if world > 1 else None
-    collectives = make_collectives(device) if world > 1 and not os.environ.get("SSW_BENCH_REPLICATED_CHEMISTRY") else None
+    # N > 1: the ranks exchange through peer-mapped arenas over NVLink (csrc/peer.cuh); torch.distributed only carries
+    # the 64-byte IPC handles and the bench's own barriers.  SSW_BENCH_HOOKS=1 runs the older NCCL-hook path instead.
+    use_hooks = world > 1 and bool(os.environ.get("SSW_BENCH_HOOKS"))
+    allreduce = make_allreduce(device) if use_hooks else None
+    collectives = make_collectives(device) if use_hooks and not os.environ.get("SSW_BENCH_REPLICATED_CHEMISTRY") else None
     shard_rank, shard_world = rank, world
     if args.emulate_shard and world == 1:
         # profiling aid: one GPU runs rank 0's direction shard of a W-rank job with a no-op all-reduce, to tune the
@@ -317,6 +320,8 @@ def run_b200(args) -> None:
         args.no_e2e = True
     sweep = Sweep(params, g, **fields, device_id=local_rank, rank=shard_rank, world_size=shard_world, allreduce=allreduce,
                   collectives=collectives)
+    if world > 1 and not use_hooks:
+        attach_peers(sweep)
     N = g.n_cells
     b_alg, f_up = algorithmic_bytes_per_update(g, sweep.directions.xyz)
 

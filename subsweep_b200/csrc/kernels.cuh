@@ -31,10 +31,6 @@ namespace ssw {
 namespace cg = cooperative_groups;
 
 constexpr int kMaxDirs = 128;
-// opt-in shared memory per block on sm_100 (227 KB).  The limit is a per-function attribute of the whole process: it is
-// always raised to the maximum, never to the size of one launch, so that handles on different threads cannot lower it
-// under each other's launches.
-constexpr int kMaxDynamicSmem = 227 * 1024;
 
 struct GridView {
     const double4 *face_geo;

@@ -1235,7 +1235,7 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
         const size_t smem_block_max = 227u * 1024u - 1024u;
         while (smem > smem_block_max && stages > 2) { --stages; smem = patch_smem(stages, stage_bytes, vmax, pc_max, smax).total; }
         if (smem > smem_block_max) throw PatchUnsupported("a macro-tile does not fit in shared memory");
-        cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem), "set max dynamic smem");
+        raise_smem_limit((const void *)kernel);
         int per_sm = 0;
         cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)threads, smem), "occupancy");
         if (per_sm < 1) throw PatchUnsupported("patch kernel does not fit on an SM");
@@ -1416,7 +1416,7 @@ inline void run_patch(Compiled &C, const double2 *cellrec, double threshold, cud
     }
     PatchKernel kernel = patch_kernel_for(C.threads, prof_dev != nullptr);
     const size_t smem = patch_smem(C.stages, C.stage_bytes, C.vmax, C.pc_max, C.smax).total;
-    cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem), "set max dynamic smem");
+    raise_smem_limit((const void *)kernel);
     void *args[] = {&a};
     // cooperative launch only to guarantee co-residency of all blocks (the done flags are polled)
     cuda_ok(cudaLaunchCooperativeKernel((const void *)kernel, dim3(C.n_blocks), dim3(C.threads), args, smem, stream),

@@ -797,6 +797,16 @@ inline void cuda_ok(cudaError_t e, const char *what) {
     if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+// Opt-in shared memory per block (227 KB on sm_100).  The limit is a per-function attribute of the whole process: it is
+// always raised to the maximum the function can have (227 KB minus its static shared memory), never to the size of one
+// launch, so that handles on different threads cannot lower it under each other's launches.
+inline void raise_smem_limit(const void *func) {
+    cudaFuncAttributes fa;
+    cuda_ok(cudaFuncGetAttributes(&fa, func), "function attributes");
+    cuda_ok(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes),
+            "set max dynamic smem");
+}
+
 inline uint32_t env_u32(const char *name, uint32_t fallback) {
     const char *v = std::getenv(name);
     if (!v || !*v) return fallback;
@@ -810,7 +820,7 @@ inline uint32_t env_u32(const char *name, uint32_t fallback) {
 inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tasks, const uint32_t *level_off_dev,
                              uint64_t n_tasks, uint32_t n_levels, int n_local_dirs, const uint32_t *pcells,
                              uint32_t n_periodic, const int32_t *pidx, const double *q_nat, int num_sms,
-                             cudaStream_t stream, uint64_t *launch_counter, bool allow_walk = false) {
+                             cudaStream_t stream, uint64_t *launch_counter, bool allow_walk = false, uint32_t default_groups = 2) {
     C.release();
     if (n_tasks >= 0x7fffff00ull) throw std::runtime_error("compile_schedule: more than 2^31 tasks per rank");
     if (n_local_dirs > 128) throw std::runtime_error("compile_schedule: more than 128 local directions");
@@ -838,7 +848,7 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
     } else {
         threads = env_u32("SSW_STREAM_THREADS", few_dirs ? 512 : 256) == 256 ? 256u : 512u;
         tile_slots = threads;
-        G = std::min<uint32_t>(env_u32("SSW_STREAM_GROUPS", few_dirs ? 1 : 2), kMaxGroups);
+        G = std::min<uint32_t>(env_u32("SSW_STREAM_GROUPS", few_dirs ? 1 : default_groups), kMaxGroups);
         G = std::max<uint32_t>(1u, std::min<uint32_t>(G, n_dl));
         want_bps = env_u32("SSW_STREAM_BPS", threads == 256 ? 4 : 2);
         want_stages = std::max<uint32_t>(1u, std::min<uint32_t>(env_u32("SSW_STREAM_STAGES", 3), kMaxStages));
@@ -1014,7 +1024,7 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
         } else {
             StreamKernel kernel = stream_kernel_for(threads, bps, false, false);
             const size_t smem = stream_smem_bytes(stages, stage_bytes);
-            cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem), "set max dynamic smem");
+            raise_smem_limit((const void *)kernel);
             cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)threads, smem), "occupancy");
         }
         if (per_sm < 1) throw std::runtime_error("compile_schedule: stream kernel does not fit on an SM");
@@ -1119,7 +1129,7 @@ inline void compile_schedule(Compiled &C, const GridView &g, const uint32_t *tas
             if (stages < unit) throw WalkUnsupported("walk form: too few tile packets fit beside the window");
             WalkKernel wk = walk_kernel_for(walk_groups, threads, false);
             const size_t smem = walk_smem_bytes(stages, stage_bytes, window);
-            cuda_ok(cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem), "set max dynamic smem");
+            raise_smem_limit((const void *)wk);
             int occ = 0;
             cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wk, (int)(walk_groups * threads) + 32 + 32 * kWalkGatherWarps, smem), "occupancy");
             if (occ < 1) throw WalkUnsupported("walk form: the kernel does not fit on an SM");
@@ -1277,7 +1287,7 @@ inline void run_walk(Compiled &C, const double *att, const double *src, double n
     }
     WalkKernel kernel = walk_kernel_for(C.walk_groups, C.threads, prof_dev != nullptr);
     const size_t smem = walk_smem_bytes(C.stages, C.stage_bytes, C.window);
-    cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem), "set max dynamic smem");
+    raise_smem_limit((const void *)kernel);
     kernel<<<C.n_blocks, C.walk_groups * C.threads + 32 + 32 * kWalkGatherWarps, smem, stream>>>(a);
     cuda_ok(cudaGetLastError(), "walk_kernel launch");
     if (prof_dev) {
@@ -1345,7 +1355,7 @@ inline void run_compiled(Compiled &C, const double2 *cellrec, double threshold, 
     }
     StreamKernel kernel = stream_kernel_for(C.threads, C.bps, prof_dev != nullptr, C.solo);
     const size_t smem = stream_smem_bytes(C.stages, C.stage_bytes);
-    cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem), "set max dynamic smem");
+    raise_smem_limit((const void *)kernel);
     void *args[] = {&a};
     // cooperative launch only to guarantee co-residency of all blocks (the level barriers spin)
     cuda_ok(cudaLaunchCooperativeKernel((const void *)kernel, dim3(C.n_blocks), dim3(C.threads), args, smem, stream),
