@@ -270,7 +270,8 @@ def workload_config(args, note: str | None = None) -> dict:
     cfg = {
         "workload": text,
         "cells": args.n ** 3, "directions": args.dirs, "timestep_levels": args.levels, "grid": args.grid,
-        "parallelism": (f"direction sharding x{args.gpus}, peer-mapped exchange over NVLink" if args.gpus > 1 else "single GPU"),
+        "parallelism": (f"direction sharding x{args.gpus}, " + ("NCCL hooks (SSW_BENCH_HOOKS)" if os.environ.get("SSW_BENCH_HOOKS")
+                                                                  else "peer-mapped exchange over NVLink") if args.gpus > 1 else "single GPU"),
         "l2": "working set (per-direction flux state + level sets, > 2 GB) is far larger than the 126 MB L2; no flush needed",
         "step": "one Sweep::run_sweeps call (all single sweeps of the level order + chemistry + level update)",
     }

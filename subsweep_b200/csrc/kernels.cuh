@@ -697,6 +697,8 @@ struct PeerChem {
     uint32_t first, n_own, n_per;
     const double *recv;         // W x n_per partial rates of the own slice
     double *att[16];            // the att array of every rank
+    unsigned int *counter[16];  // the arrival counter of every rank (peer.cuh)
+    unsigned int *blocks_done;  // this handle's block check-in counter
 };
 
 __global__ void __launch_bounds__(128)
@@ -779,6 +781,18 @@ chemistry_kernel(CellView cv, const uint32_t *__restrict__ act_list, uint32_t n_
         atomicAdd(&stats->failures, s_fail);
         atomicAdd(&stats->cells, s_cells);
         atomicMax(&stats->max_depth, s_depth);
+    }
+    if (pc.world > 1) {
+        // the new absorption factors are in every rank's array: tell them (the all-gather's completion signal, from the
+        // last block of this kernel; see peer_signal_tail)
+        __syncthreads();
+        if (threadIdx.x == 0) __threadfence_system();   // cumulative over the block's stores (seen through the barrier)
+        if (threadIdx.x == 0 && atomicAdd(pc.blocks_done, 1u) == gridDim.x - 1u) {
+            *pc.blocks_done = 0u;
+            __threadfence_system();
+            for (int p = 0; p < pc.world; ++p)
+                asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(pc.counter[p]) : "memory");
+        }
     }
 }
 

@@ -17,11 +17,12 @@
 //                   per-level histograms travel the same way;
 //   read-back       the reading rank pulls the other owners' slices.
 //
-// Ordering between ranks: a signal is one 4-byte epoch number stored with release semantics at system scope into the
-// peer's flag word after a system-scope fence (one tiny kernel behind the producer on the same stream); the wait is a
-// stream memory operation (cuStreamWaitValue32 on the rank's own flag words -- no SM is held while waiting, so ranks
-// that share a device in the tests cannot starve each other), or a one-warp polling kernel where stream memory
-// operations are unavailable.
+// Ordering between ranks: every rank has ONE arrival counter in its arena.  A signal is an atomic increment with
+// release semantics at system scope of every rank's counter (red.release.sys over NVLink), issued behind a
+// system-scope fence by the last thread block of the kernel that produced the data (peer_signal_tail) -- no extra
+// launch -- or by a one-warp kernel.  The wait for synchronisation point e is "own counter >= e * W": one stream memory
+// operation (cuStreamWaitValue32 -- no SM is held while waiting), a host poll where ranks share a device (tests), or a
+// one-warp polling kernel where stream memory operations are unavailable.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -30,7 +31,7 @@
 namespace ssw {
 
 constexpr int kMaxPeers = 16;
-constexpr uint32_t kPeerFlagStride = 128;   // bytes between the flag words of two source ranks
+constexpr uint32_t kPeerFlagStride = 128;   // bytes reserved per flag word
 constexpr uint32_t kPeerHistWords = 40;     // u64 per source rank: 32 level counts, [32] = cells whose level changed
 
 struct PeerLayout {   // byte offsets into an arena; identical on every rank
@@ -69,27 +70,46 @@ inline PeerLayout peer_layout(uint32_t n_cells, int world) {
     return L;
 }
 
-// signal: "everything this rank queued on its stream before this kernel is visible" -> every peer's flag word
+__device__ __forceinline__ void peer_arrive(const PeerTable &t, int p) {
+    unsigned int *counter = reinterpret_cast<unsigned int *>(t.base[p] + t.L.flags);
+    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+
+// signal: "everything this rank queued on its stream before this kernel is visible" -> every rank's arrival counter
 __global__ void __launch_bounds__(32)
-peer_signal_kernel(PeerTable t, uint32_t epoch) {
+peer_signal_kernel(PeerTable t) {
     const int p = threadIdx.x;
     if (p >= t.world) return;
     __threadfence_system();
-    unsigned int *flag = reinterpret_cast<unsigned int *>(t.base[p] + t.L.flags + (uint64_t)t.rank * kPeerFlagStride);
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+    peer_arrive(t, p);
 }
 
-// fallback wait (no stream memory operations): one warp polls the rank's own flag words; bounded, a lost peer traps
+// The same signal from the tail of the kernel that produced the data (called by every thread of every block, at the
+// end): each block fences its stores at system scope and checks in; the last one to do so signals all ranks.
+// `blocks_done` is a zero-initialised device counter of the handle (reset here for the next kernel).
+__device__ __forceinline__ void peer_signal_tail(const PeerTable &t, unsigned int *blocks_done) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();   // cumulative: orders the block's stores (seen through the barrier) before the check-in
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(blocks_done, 1u) == total - 1u) {
+            *blocks_done = 0u;
+            __threadfence_system();
+            for (int p = 0; p < t.world; ++p) peer_arrive(t, p);
+        }
+    }
+}
+
+// fallback wait (no stream memory operations): one thread polls the rank's own counter; bounded, a lost peer traps
 __global__ void __launch_bounds__(32)
-peer_wait_kernel(PeerTable t, uint32_t epoch) {
-    const int p = threadIdx.x;
-    if (p >= t.world) return;
-    const unsigned int *flag = reinterpret_cast<const unsigned int *>(t.base[t.rank] + t.L.flags + (uint64_t)p * kPeerFlagStride);
+peer_wait_kernel(PeerTable t, uint32_t target) {
+    if (threadIdx.x != 0) return;
+    const unsigned int *counter = reinterpret_cast<const unsigned int *>(t.base[t.rank] + t.L.flags);
     const long long t0 = clock64();
     for (;;) {
         unsigned int v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if ((int32_t)(v - epoch) >= 0) break;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if ((int32_t)(v - target) >= 0) break;
         if (clock64() - t0 > 60000000000ll) __trap();   // ~30 s
         __nanosleep(200);
     }
@@ -97,22 +117,27 @@ peer_wait_kernel(PeerTable t, uint32_t epoch) {
 
 // partial rates of the active cells -> the owners' receive buffers
 __global__ void __launch_bounds__(256)
-peer_push_rates_kernel(PeerTable t, const uint32_t *__restrict__ act_list, uint32_t n_act, const double *__restrict__ rate_act) {
+peer_push_rates_kernel(PeerTable t, const uint32_t *__restrict__ act_list, uint32_t n_act, const double *__restrict__ rate_act,
+                       unsigned int *blocks_done) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_act) return;
-    const uint32_t c = act_list ? act_list[k] : k;
-    const uint32_t owner = c / t.n_per;
-    t.f64((int)owner, t.L.recv)[(uint64_t)t.rank * t.n_per + (c - owner * t.n_per)] = rate_act[k];
+    if (k < n_act) {
+        const uint32_t c = act_list ? act_list[k] : k;
+        const uint32_t owner = c / t.n_per;
+        t.f64((int)owner, t.L.recv)[(uint64_t)t.rank * t.n_per + (c - owner * t.n_per)] = rate_act[k];
+    }
+    peer_signal_tail(t, blocks_done);   // the reduce-scatter and its completion signal in one launch
 }
 
 // per-level histogram of this rank's slice -> every rank
 __global__ void __launch_bounds__(64)
-peer_hist_push_kernel(PeerTable t, const unsigned long long *__restrict__ hist) {
+peer_hist_push_kernel(PeerTable t, const unsigned long long *__restrict__ hist, unsigned int *blocks_done) {
     const uint32_t i = threadIdx.x;
-    if (i >= 33) return;
-    const unsigned long long v = hist[i];
-    for (int p = 0; p < t.world; ++p)
-        reinterpret_cast<unsigned long long *>(t.base[p] + t.L.hist)[(uint64_t)t.rank * kPeerHistWords + i] = v;
+    if (i < 33) {
+        const unsigned long long v = hist[i];
+        for (int p = 0; p < t.world; ++p)
+            reinterpret_cast<unsigned long long *>(t.base[p] + t.L.hist)[(uint64_t)t.rank * kPeerHistWords + i] = v;
+    }
+    peer_signal_tail(t, blocks_done);   // also publishes the levels the kernel before this one stored into every rank
 }
 
 // a replicated-per-cell value of this rank's slice -> every other rank (absorption factors after ssw_set_inputs)

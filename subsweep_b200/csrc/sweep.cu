@@ -189,7 +189,8 @@ struct Sweep {
     DevBuf<unsigned char> arena;
     PeerTable pt{};
     bool peers = false;            // the arenas of all ranks are attached: no hooks, no collective library
-    uint32_t peer_epoch = 0;
+    uint32_t peer_epoch = 0;       // synchronisation points so far; every rank's counter reaches peer_epoch * world_size
+    DevBuf<unsigned int> blocks_done;
     std::vector<void *> ipc_opened;
     typedef int (*StreamWaitValue32)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
     StreamWaitValue32 stream_wait_value32 = nullptr;
@@ -341,6 +342,7 @@ struct Sweep {
     // peer-mapped exchange (peer.cuh)
     void peer_attach(void *const *bases);
     void peer_sync_point();
+    void peer_wait();
     void peer_allreduce(double *buf, uint64_t n);
     void peer_pull(uint64_t off);
     PeerChem peer_chem() const;
@@ -494,6 +496,7 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     cell_tmp.alloc(N);
     cell_tmp2.alloc(N);
     hist.alloc(33);
+    blocks_done.alloc(1); blocks_done.zero(stream);
     chem_stats.alloc(1); chem_stats.zero(stream);
     CUDA_CHECK(cudaStreamSynchronize(stream));  // host vectors go out of scope
 
@@ -771,35 +774,35 @@ void Sweep::peer_attach(void *const *bases) {
 // every rank signals every rank, then waits for everybody's signal: what this rank queued before the point is visible
 // to all ranks behind it, and vice versa
 void Sweep::peer_sync_point() {
+    peer_signal_kernel<<<1, 32, 0, stream>>>(pt);
+    launched();
+    peer_wait();
+}
+
+// the wait half; the signal was given by peer_signal_kernel or by the tail of the producing kernel (peer_signal_tail)
+void Sweep::peer_wait() {
     const size_t t = tic(T_ALLREDUCE);
     ++peer_epoch;
-    peer_signal_kernel<<<1, 32, 0, stream>>>(pt, peer_epoch);
-    launched();
+    const uint32_t target = peer_epoch * (uint32_t)P.world_size;
     if (peer_wait_mode == 0) {
-        for (int r = 0; r < P.world_size; ++r) {
-            const unsigned long long addr = (unsigned long long)(uintptr_t)(arena.p + pt.L.flags + (uint64_t)r * kPeerFlagStride);
-            const int rc = stream_wait_value32(stream, addr, peer_epoch, /*CU_STREAM_WAIT_VALUE_GEQ*/ 0u);
-            if (rc != 0) fail(SSW_E_COMM, "cuStreamWaitValue32 failed (%d)", rc);
-        }
+        const unsigned long long addr = (unsigned long long)(uintptr_t)(arena.p + pt.L.flags);
+        const int rc = stream_wait_value32(stream, addr, target, /*CU_STREAM_WAIT_VALUE_GEQ*/ 0u);
+        if (rc != 0) fail(SSW_E_COMM, "cuStreamWaitValue32 failed (%d)", rc);
     } else if (peer_wait_mode == 1) {
         const auto t00 = std::chrono::steady_clock::now();
         CUDA_CHECK(cudaStreamSynchronize(stream));   // my signal is out
         if (!flags_host) CUDA_CHECK(cudaHostAlloc((void **)&flags_host, (size_t)kMaxPeers * kPeerFlagStride, cudaHostAllocDefault));
         unsigned char *flags_h = flags_host;
-        const size_t flags_bytes = (size_t)P.world_size * kPeerFlagStride;
+        const size_t flags_bytes = sizeof(uint32_t);
         const auto t0 = std::chrono::steady_clock::now();
         unsigned long polls = 0;
         for (;;) {
             ++polls;
             CUDA_CHECK(cudaMemcpyAsync(flags_h, arena.p + pt.L.flags, flags_bytes, cudaMemcpyDeviceToHost, aux_stream));
             CUDA_CHECK(cudaStreamSynchronize(aux_stream));
-            bool ok = true;
-            for (int r = 0; r < P.world_size && ok; ++r) {
-                uint32_t v;
-                std::memcpy(&v, flags_h + (size_t)r * kPeerFlagStride, sizeof v);
-                ok = (int32_t)(v - peer_epoch) >= 0;
-            }
-            if (ok) break;
+            uint32_t v;
+            std::memcpy(&v, flags_h, sizeof v);
+            if ((int32_t)(v - target) >= 0) break;
             if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60))
                 fail(SSW_E_COMM, "peer exchange: a rank did not reach synchronisation point %u within 60 s", peer_epoch);
             std::this_thread::yield();
@@ -810,7 +813,7 @@ void Sweep::peer_sync_point() {
                     std::chrono::duration<double, std::milli>(t0 - t00).count(), std::chrono::duration<double, std::milli>(t1 - t0).count(), polls);
         }
     } else {
-        peer_wait_kernel<<<1, 32, 0, stream>>>(pt, peer_epoch);
+        peer_wait_kernel<<<1, 32, 0, stream>>>(pt, target);
         launched();
     }
     CUDA_CHECK(cudaGetLastError());
@@ -841,7 +844,11 @@ PeerChem Sweep::peer_chem() const {
     pc.n_own = pt.n_own();
     pc.n_per = pt.n_per;
     pc.recv = pt.f64(P.rank, pt.L.recv);
-    for (int r = 0; r < P.world_size; ++r) pc.att[r] = pt.f64(r, pt.L.att);
+    for (int r = 0; r < P.world_size; ++r) {
+        pc.att[r] = pt.f64(r, pt.L.att);
+        pc.counter[r] = reinterpret_cast<unsigned int *>(pt.base[r] + pt.L.flags);
+    }
+    pc.blocks_done = blocks_done.p;
     return pc;
 }
 
@@ -1083,16 +1090,19 @@ void Sweep::single_sweep(int cur) {
     if (P.world_size > 1 && peers) {
         // peer-mapped exchange: partial rates straight into the owners' receive buffers, chemistry on the owner, new
         // absorption factors straight into every rank's array (peer.cuh)
-        peer_push_rates_kernel<<<cdiv(n_act, 256), 256, 0, stream>>>(pt, act, n_act, rate_act.p);
+        peer_push_rates_kernel<<<cdiv(n_act, 256), 256, 0, stream>>>(pt, act, n_act, rate_act.p, blocks_done.p);
         launched();
-        peer_sync_point();
+        peer_wait();                      // everybody's partial rates of my cells have arrived
         const uint32_t n_launch = all ? pt.n_own() : n_act;
-        if (n_launch) {
+        if (n_launch) {                   // the kernel's tail signals every rank
             chemistry_kernel<<<cdiv(n_launch, 128), 128, 0, stream>>>(cell_view(), act, n_launch, nullptr, cp, chem_stats.p,
                                                                        all ? pt.first() : 0u, peer_chem());
             launched();
+        } else {
+            peer_signal_kernel<<<1, 32, 0, stream>>>(pt);
+            launched();
         }
-        peer_sync_point();
+        peer_wait();                      // everybody's new absorption factors are in my array
     } else if (all && P.world_size > 1 && collective) {
         // all cells active on W ranks: reduce-scatter the partial rates, update the own slice of cells, all-gather
         // the results -- the chemistry is not replicated W times, and every rank ends with bit-identical state
@@ -1132,9 +1142,9 @@ void Sweep::update_timestep_levels() {
     unsigned long long h[33];
     if (peers) {
         // the owners pushed the new levels into every rank's array; the per-level counts travel the same way
-        peer_hist_push_kernel<<<1, 64, 0, stream>>>(pt, hist.p);
+        peer_hist_push_kernel<<<1, 64, 0, stream>>>(pt, hist.p, blocks_done.p);
         launched();
-        peer_sync_point();
+        peer_wait();
         std::vector<unsigned long long> all_h((size_t)P.world_size * kPeerHistWords);
         CUDA_CHECK(cudaMemcpyAsync(all_h.data(), arena.p + pt.L.hist, sizeof(unsigned long long) * all_h.size(),
                                    cudaMemcpyDeviceToHost, stream));

@@ -1,6 +1,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -x 2>&1 | tail -6
-rm -f gpurun_out/r2o_tune.jsonl
-timeout 400 python tools/tune_stream.py --n 128 --grid voronoi --out gpurun_out/r2o_tune.jsonl - 2>&1 | tail -1 | cut -c1-300
-timeout 300 python tools/tune_stream.py --n 64 --grid voronoi --out gpurun_out/r2o_tune.jsonl - SSW_WALK=0 SSW_WALK=1 2>&1 | tail -3 | cut -c1-300
+timeout 300 python -m pytest tests/test_gpu_sharded.py -m gpu -q --timeout 120 -x 2>&1 | tail -4
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2q_n2_peers.json 2> gpurun_out/r2q_n2_peers.err
+tail -c 400 gpurun_out/r2q_n2_peers.err; cat gpurun_out/r2q_n2_peers.json | cut -c1-300
