@@ -506,7 +506,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
-    ap.add_argument("--n", type=int, default=128, help="cells per dimension")
+    ap.add_argument("--n", "--cells-per-dim", dest="n", type=int, default=128,
+                    help="cells per dimension (use the long form under torchrun, whose own parser chokes on --n)")
     ap.add_argument("--grid", choices=("cartesian", "voronoi"), default="cartesian")
     ap.add_argument("--dirs", type=int, default=84)
     ap.add_argument("--levels", type=int, default=4)

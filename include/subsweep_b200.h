@@ -150,6 +150,14 @@ int ssw_set_collectives(ssw_handle *h, ssw_collective_fn fn, void *ctx);
  * cyclically keep the level-barrier form; ssw_patch_note() says why (empty string: patch form in use
  * or not tried). */
 int ssw_set_cell_positions(ssw_handle *h, const double *xyz /* N x 3 */);
+/* rotate_directions_system (src/sweep/direction/mod.rs:158-174, `sweep.rotate_directions`): replace the direction set
+ * by another one of the same size (the host rotates the bins; the Python mirror does it with the reference's
+ * axis-angle construction).  New direction i continues with the outgoing rates of the old direction it is best
+ * aligned with (largest dot product).  The reference's `remap` (:190-205) intends that kernel but assigns instead of
+ * accumulating, which wipes all but the last direction's state; this library implements the intended remap and does NOT
+ * reproduce the bug.  Level sets depend on the directions: after the first call nothing direction-dependent is
+ * compiled or cached any more (every sweep peels its level sets while it solves).  Single rank only. */
+int ssw_set_directions(ssw_handle *h, const double *dirs_xyz /* D x 3 */);
 const char *ssw_patch_note(ssw_handle *h);
 
 /* -- direction sharding without hooks: peer-mapped exchange over NVLink / NVSwitch ---------------------- */
@@ -250,7 +258,9 @@ typedef enum ssw_stat {
     SSW_STAT_CHEM_MAX_DEPTH = 9,
     SSW_STAT_PATCH_MACRO_TILES = 10, /* macro-tiles of the patch-ordered all-cells sweep (0: not in use) */
     SSW_STAT_PATCH_LEVELS = 11,      /* dependent macro-tile levels (vs SSW_STAT_WAVEFRONT_LEVELS)       */
-    SSW_STAT_PATCH_PHASES = 12       /* phases of the macro-tiles (1: the patch graph was acyclic)       */
+    SSW_STAT_PATCH_PHASES = 12,      /* phases of the macro-tiles (1: the patch graph was acyclic)       */
+    SSW_STAT_WALK_WINDOW = 13,       /* walk form of the all-cells sweep: slots of the shared-memory window (0: not in use) */
+    SSW_STAT_WALK_NEAR_PERMILLE = 14 /* walk form: upwind entries read from the window, per thousand     */
 } ssw_stat;
 int ssw_get_stat(ssw_handle *h, ssw_stat which, uint64_t *out);
 

@@ -87,6 +87,7 @@ SYMBOLS = {
     "ssw_destroy": (None, [H]),
     "ssw_set_allreduce": (C.c_int, [H, ALLREDUCE_FN, C.c_void_p]),
     "ssw_set_collectives": (C.c_int, [H, COLLECTIVE_FN, C.c_void_p]),
+    "ssw_set_directions": (C.c_int, [H, c_double_p]),
     "ssw_peer_arena": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "ssw_peer_export": (C.c_int, [H, C.c_void_p]),
     "ssw_peer_attach_ipc": (C.c_int, [H, C.c_void_p]),

@@ -218,28 +218,40 @@ __device__ __forceinline__ void solve_task(const SweepArgs &a, uint32_t task, ui
     }
     if (BUILD && valid && wlevel_dbg) wlevel_dbg[c] = wave;
     if (BUILD) {
-        // handle_local_neighbour (src/sweep/mod.rs:487-503): release downwind active neighbours
+        // handle_local_neighbour (src/sweep/mod.rs:487-503): release downwind active neighbours.  Faces in chunks of
+        // kChunk: geometry and neighbour of the whole chunk are loaded together, then the neighbours' timestep levels,
+        // then the counters are decremented and the released tasks pushed -- three dependent memory round trips per
+        // chunk instead of three per face (a wavefront level of the build costs a few microseconds, not tens).  The
+        // pushes are warp-synchronous: every lane of the warp runs the same number of rounds.
         __syncwarp();
-        uint32_t f = f0;
-        while (true) {
-            // find this thread's next downwind Local active face (warp-synchronous push needs
-            // all lanes to take part in every round)
-            bool have = false;
-            uint32_t nb = 0;
-            while (valid && f < f1) {
-                const uint32_t ff = f++;
-                if (a.g.face_kind[ff] != 0) continue;
-                const double d = dot_dir(ld_geo(a.g.face_geo + ff), dx, dy, dz);
-                if (!(d > 0.0)) continue;
-                nb = (uint32_t)a.g.face_nb[ff];
-                if (a.level[nb] < a.cur) continue;
-                have = true;
-                break;
+        constexpr int kChunk = 8;
+        uint32_t n_faces = valid ? f1 - f0 : 0u;
+        for (int o = 16; o > 0; o >>= 1) n_faces = max(n_faces, __shfl_xor_sync(0xffffffffu, n_faces, o));
+        for (uint32_t fb = 0; fb < n_faces; fb += kChunk) {
+            uint32_t nb[kChunk];
+            bool cand[kChunk];
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                const uint32_t f = f0 + fb + j;
+                nb[j] = 0;
+                cand[j] = false;
+                if (valid && f < f1) {
+                    const double d = dot_dir(ld_geo(a.g.face_geo + f), dx, dy, dz);
+                    nb[j] = (uint32_t)a.g.face_nb[f];
+                    cand[j] = a.g.face_kind[f] == 0 && d > 0.0;
+                }
             }
-            if (__ballot_sync(0xffffffffu, have) == 0) break;
-            bool ready = false;
-            if (have) ready = atomicSub(a.missing + (size_t)dl * N + nb, 1) == 1;
-            warp_push(queue, push_base, push_counter, ready, dl * N + nb);
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j)
+                if (cand[j]) cand[j] = a.level[nb[j]] >= a.cur;
+            bool ready[kChunk];
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) ready[j] = cand[j] && atomicSub(a.missing + (size_t)dl * N + nb[j], 1) == 1;
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                if (__ballot_sync(0xffffffffu, ready[j]) == 0) continue;   // uniform across the warp
+                warp_push(queue, push_base, push_counter, ready[j], dl * N + nb[j]);
+            }
         }
     }
 }
@@ -474,9 +486,8 @@ __device__ __forceinline__ void mini_solve(const SweepArgs &a, const MiniView &m
     const uint32_t dl = p.task / N, c = p.task - dl * N;
     __stcg(a.incoming + (size_t)dl * N + c, inc);
 }
-__global__ void __launch_bounds__(kMiniSmallThreads)
-mini_replay_small_kernel(SweepArgs a, MiniView m, const uint32_t *__restrict__ queue,
-                         const uint32_t *__restrict__ level_off, uint32_t n_levels) {
+__device__ __forceinline__ void mini_replay_small_body(const SweepArgs &a, const MiniView &m, const uint32_t *__restrict__ queue,
+                                                       const uint32_t *__restrict__ level_off, uint32_t n_levels) {
     if (n_levels == 0) return;
     uint32_t s = level_off[0], e = level_off[1];
     MiniPre cur = mini_prefetch(a, m, queue, s + threadIdx.x, s + threadIdx.x < e);
@@ -491,6 +502,11 @@ mini_replay_small_kernel(SweepArgs a, MiniView m, const uint32_t *__restrict__ q
         s = s2;
         e = e2;
     }
+}
+__global__ void __launch_bounds__(kMiniSmallThreads)
+mini_replay_small_kernel(SweepArgs a, MiniView m, const uint32_t *__restrict__ queue,
+                         const uint32_t *__restrict__ level_off, uint32_t n_levels) {
+    mini_replay_small_body(a, m, queue, level_off, n_levels);
 }
 
 __global__ void __launch_bounds__(256)
@@ -536,6 +552,26 @@ periodic_gather_kernel(GridView g, const uint32_t *__restrict__ pcells, uint32_t
         if (d < 0.0) acc += st.load_q(dl, (uint32_t)g.face_nb[f]) * (g.face_rev[f] * (-d));
     }
     dst[(size_t)dl * n_periodic + p] = acc;
+}
+
+// ssw_set_directions: the flux state for a new direction set.  New direction dl takes the outgoing rate of the old
+// direction map[dl] it is best aligned with; q = out / sum_downwind(A n.d) with the NEW directions (g.dirs).
+__global__ void __launch_bounds__(256)
+remap_directions_kernel(GridView g, const double *__restrict__ out_old_cell_major, const int32_t *__restrict__ map,
+                        int n_local_dirs, double *__restrict__ q_new) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.n_cells) return;
+    for (int dl = 0; dl < n_local_dirs; ++dl) {
+        const double dx = g.dirs[3 * dl], dy = g.dirs[3 * dl + 1], dz = g.dirs[3 * dl + 2];
+        double ttot = 0.0;
+        for (uint32_t f = g.face_off[c]; f < g.face_off[c + 1]; ++f) {
+            const double4 geo = ld_geo(g.face_geo + f);
+            const double d = dot_dir(geo, dx, dy, dz);
+            if (d > 0.0) ttot += geo.w * d;
+        }
+        const double out = out_old_cell_major[(size_t)c * n_local_dirs + map[dl]];
+        q_new[(size_t)dl * g.n_cells + c] = ttot > 0.0 ? out / ttot : 0.0;
+    }
 }
 
 // incoming_total_rate for every (cell, dir) from the current q (read-back / photon_rate,
@@ -701,15 +737,32 @@ struct PeerChem {
     unsigned int *blocks_done;  // this handle's block check-in counter
 };
 
+// Work balancing: the substep count of a cell spans three decades at an ionization front and a warp runs as long as
+// its slowest lane (measured on the front workload: 8.3 of 32 lanes active on average).  `order` (optional) is a
+// permutation of the launch indices sorted by the substep count the cell needed LAST time (chem_order_*_kernel +
+// radix sort), so the lanes of a warp hold cells of similar cost.  Every cell's arithmetic is independent of which
+// thread runs it: results are bit-identical with and without.
+__global__ void __launch_bounds__(256)
+chem_order_keys_kernel(const uint32_t *__restrict__ act_list, uint32_t n, uint32_t first_cell, const uint16_t *__restrict__ last_attempts,
+                       uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t c = act_list ? act_list[k] : first_cell + k;
+    keys[k] = 65535u - last_attempts[c];   // heaviest first: the long warps start early
+    vals[k] = k;
+}
+
 __global__ void __launch_bounds__(128)
 chemistry_kernel(CellView cv, const uint32_t *__restrict__ act_list, uint32_t n_act,
-                 const double *__restrict__ rate_act, ChemParams cp, ChemStats *stats, uint32_t first_cell, PeerChem pc) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+                 const double *__restrict__ rate_act, ChemParams cp, ChemStats *stats, uint32_t first_cell, PeerChem pc,
+                 const uint32_t *__restrict__ order, uint16_t *__restrict__ last_attempts) {
+    const uint32_t kk = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long attempts = 0;
     unsigned int depth = 0, failed = 0, mine = 0;
-    bool active = k < n_act;
-    uint32_t c = 0;
+    bool active = kk < n_act;
+    uint32_t c = 0, k = kk;
     if (active) {
+        if (order) k = order[kk];
         c = act_list ? act_list[k] : first_cell + k;   // no list: the contiguous cells [first_cell, first_cell + n_act)
         if (pc.world > 1 && (c < pc.first || c >= pc.first + pc.n_own)) active = false;   // another rank owns the cell
     }
@@ -757,6 +810,7 @@ chemistry_kernel(CellView cv, const uint32_t *__restrict__ act_list, uint32_t n_
         attempts = r.attempts;
         depth = (unsigned)r.max_depth;
         failed = (unsigned)r.failed;
+        last_attempts[c] = (uint16_t)(attempts < 65535ull ? attempts : 65535ull);
     }
     // block-level statistics
     __shared__ unsigned long long s_att, s_fail, s_cells;

@@ -24,6 +24,7 @@
 #include "stream.cuh"
 #include "patch.cuh"
 #include "peer.cuh"
+#include "small.cuh"
 
 namespace ssw {
 
@@ -119,6 +120,23 @@ struct Schedule {
     MiniView mini_view() const { return MiniView{m_off.p, m_src.p, m_w.p, m_self.p, m_ttot.p}; }
 };
 
+// SSW_TIME_SCHED=1: wall-clock time of the pieces of a schedule rebuild (synchronises the stream around each piece)
+struct SchedProbe {
+    cudaStream_t st;
+    const char *what;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    SchedProbe(cudaStream_t s, const char *w) : st(s), what(w), on(std::getenv("SSW_TIME_SCHED") != nullptr) {
+        if (on) { cudaStreamSynchronize(st); t0 = std::chrono::steady_clock::now(); }
+    }
+    ~SchedProbe() {
+        if (on) {
+            cudaStreamSynchronize(st);
+            fprintf(stderr, "[sched] %-22s %.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        }
+    }
+};
+
 enum TimerCat { T_SWEEP = 0, T_CHEM, T_LEVELS, T_SCHED, T_ALLREDUCE, T_KERNEL, T_STEP, T_COUNT };
 
 struct Sweep {
@@ -167,6 +185,10 @@ struct Sweep {
     DevBuf<double2> cellrec;
     DevBuf<unsigned long long> hist;
     DevBuf<ChemStats> chem_stats;
+    DevBuf<uint16_t> last_attempts;          // substep attempts of every cell's last chemistry update
+    DevBuf<uint32_t> order_keys, order_keys_out, order_vals, order_vals_out;
+    bool chem_balance = false;               // sort the cells of a launch by their last substep count
+    uint64_t chem_prev_attempts = 0, chem_prev_cells = 0;
     DevBuf<int32_t> wlevel;
 
     // TimestepState (src/sweep/timestep_state.rs:4-9)
@@ -319,6 +341,8 @@ struct Sweep {
     void create(const ssw_params *p, const ssw_grid *g, const double *density, const double *xhii,
                 const double *temperature, const double *source);
     void set_positions(const double *xyz);
+    void set_directions(const double *dirs_xyz);
+    bool rotating = false;   // the directions change between steps (ssw_set_directions): nothing direction-dependent is compiled
     PatchGrid patch_view() const {
         PatchGrid pg;
         pg.patch_of = patch_of.p; pg.lidx = patch_lidx.p; pg.patch_off = patch_off.p; pg.patch_cells = patch_cells.p;
@@ -340,6 +364,8 @@ struct Sweep {
     uint32_t cells_per_rank() const { return (uint32_t)(((uint64_t)N + P.world_size - 1) / P.world_size); }
     void run_collective(int op, double *buf, uint64_t n_per_rank);
     // peer-mapped exchange (peer.cuh)
+    void launch_chemistry(const uint32_t *act, uint32_t n, const double *rate, uint32_t first_cell, const ChemParams &cp,
+                          const PeerChem &pc);
     void peer_attach(void *const *bases);
     void peer_sync_point();
     void peer_wait();
@@ -498,6 +524,7 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     hist.alloc(33);
     blocks_done.alloc(1); blocks_done.zero(stream);
     chem_stats.alloc(1); chem_stats.zero(stream);
+    last_attempts.alloc(N); last_attempts.zero(stream);
     CUDA_CHECK(cudaStreamSynchronize(stream));  // host vectors go out of scope
 
     bind();
@@ -613,6 +640,48 @@ void Sweep::set_positions(const double *xyz) {
     n_patches = Pn;
     patch_max_cells = mx;
     have_patches = true;
+}
+
+// rotate_directions_system (src/sweep/direction/mod.rs:158-174): a new direction set of the same size.  The flux state
+// follows: new direction i continues with the outgoing rates of the old direction it is best aligned with.  (The
+// reference's `remap`, :190-205, intends the same kernel but ASSIGNS inside its double loop, `values[i] = old[j] *
+// kernel[i][j]`, so that only the last old direction survives -- that bug is not reproduced.)  incoming_total_rate and
+// periodic_source need no remap here: the gather form derives them from the neighbours' outgoing rates.
+void Sweep::set_directions(const double *dirs_xyz) {
+    if (!dirs_xyz) fail(SSW_E_INVALID, "null directions");
+    if (P.world_size > 1) fail(SSW_E_INVALID, "ssw_set_directions is not available under direction sharding");
+    bind();
+    // the outgoing rates under the old directions, cell-major
+    DevBuf<double> out_old;
+    out_old.alloc((size_t)N * Dl);
+    dir_state_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), state_view(), 1, Dl, out_old.p, nullptr);
+    launched();
+    std::vector<int32_t> map(D);
+    for (int i = 0; i < D; ++i) {
+        double best = -std::numeric_limits<double>::infinity();
+        for (int j = 0; j < D; ++j) {
+            const double dot = dirs_xyz[3 * i] * dirs_all[3 * j] + dirs_xyz[3 * i + 1] * dirs_all[3 * j + 1] +
+                               dirs_xyz[3 * i + 2] * dirs_all[3 * j + 2];
+            if (dot > best) { best = dot; map[i] = j; }
+        }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    // everything compiled or cached for the old directions goes
+    state = nullptr;
+    for (auto &sc : sched) sc.reset(new Schedule());
+    levels_version++;
+    photon_valid = false;
+    rotating = true;
+    dirs_all.assign(dirs_xyz, dirs_xyz + 3 * (size_t)D);
+    dirs_dev.upload(dirs_all.data(), 3 * (size_t)D, stream);
+    DevBuf<int32_t> map_dev;
+    map_dev.alloc(D);
+    map_dev.upload(map.data(), D, stream);
+    if (!q.p) q.alloc((size_t)N * Dl);
+    remap_directions_kernel<<<cdiv(N, 256), 256, 0, stream>>>(grid_view(), out_old.p, map_dev.p, Dl, q.p);
+    launched();
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
 void Sweep::refresh_histogram() {
@@ -877,6 +946,29 @@ void Sweep::run_collective(int op, double *buf, uint64_t n_per_rank) {
     toc(t);
 }
 
+// HydrogenOnly::update_abundances over the cells of one launch (src/sweep/mod.rs:559-572).  When the last step showed
+// substepping (more attempts than cells) the launch order is sorted by each cell's last substep count.
+void Sweep::launch_chemistry(const uint32_t *act, uint32_t n, const double *rate, uint32_t first_cell, const ChemParams &cp,
+                             const PeerChem &pc) {
+    if (n == 0) return;
+    const uint32_t *order = nullptr;
+    if (chem_balance && n >= 2048) {
+        order_keys.ensure(n); order_keys_out.ensure(n); order_vals.ensure(n); order_vals_out.ensure(n);
+        chem_order_keys_kernel<<<cdiv(n, 256), 256, 0, stream>>>(act, n, first_cell, last_attempts.p, order_keys.p, order_vals.p);
+        size_t bytes = 0;
+        CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, order_keys.p, order_keys_out.p, order_vals.p, order_vals_out.p,
+                                                   (int)n, 0, 16, stream));
+        cub_temp.ensure(bytes);
+        CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cub_temp.p, bytes, order_keys.p, order_keys_out.p, order_vals.p, order_vals_out.p,
+                                                   (int)n, 0, 16, stream));
+        launched(3);
+        order = order_vals_out.p;
+    }
+    chemistry_kernel<<<cdiv(n, 128), 128, 0, stream>>>(cell_view(), act, n, rate, cp, chem_stats.p, first_cell, pc, order,
+                                                       last_attempts.p);
+    launched();
+}
+
 // Sweep::single_sweep (src/sweep/mod.rs:274-289)
 void Sweep::single_sweep(int cur) {
     const uint64_t n_act64 = count_at_least(cur);
@@ -889,7 +981,7 @@ void Sweep::single_sweep(int cur) {
                        (cache_ok && S.valid && S.n_act == n_act && (all || S.version == levels_version));
     const size_t t_sweep = tic(T_SWEEP, cur);
 
-    const bool use_compiled = reuse && all && !(P.flags & SSW_FLAG_NO_COMPILED_PATH) && compiled_supported();
+    const bool use_compiled = reuse && all && !rotating && !(P.flags & SSW_FLAG_NO_COMPILED_PATH) && compiled_supported();
     if (!reuse) {
         S.valid = false;
         S.mini_valid = false;
@@ -897,7 +989,10 @@ void Sweep::single_sweep(int cur) {
         S.n_act = n_act;
         if (!all) {
             const size_t t_list = tic(T_SCHED);
-            build_active_list(S, cur);
+            {
+                SchedProbe pr(stream, "active list");
+                build_active_list(S, cur);
+            }
             toc(t_list);
         }
     }
@@ -905,12 +1000,31 @@ void Sweep::single_sweep(int cur) {
     // periodic_source as the tasks of this sweep will read it (lagged); the
     // compiled path reads the donors' previous outgoing rates directly (stream.cuh).  A partial
     // active set only refreshes the rows of its own cells.
-    if (!use_compiled) gather_periodic(per_lag.p, act, n_act);
+    // A small active set whose level sets are cached runs as ONE launch (small.cuh): lagged periodic rows, replay,
+    // photon_rate bookkeeping, new periodic rows, rate fold and -- under peer-mapped sharding, where it is the default --
+    // the hand-over of the partial rates to their owners.  (On one GPU the chain of small kernels is as fast: measured.)
+    bool fused_small = false;
+    if (reuse && !all && !use_compiled && S.n_tasks > 0 && S.n_tasks <= (64u << 20) && S.max_level_tasks <= 2048 &&
+        (uint64_t)n_act * Dl <= 65536 && (uint64_t)S.n_touch * Dl <= 262144 &&
+        (P.world_size == 1 || peers) && stream_env_u32("SSW_FUSED_SMALL", peers ? 1 : 0)) {
+        if (!S.mini_valid || S.mini_slot_state != (state != nullptr)) {
+            const size_t t_sched = tic(T_SCHED);
+            build_mini(S);
+            toc(t_sched);
+        }
+        fused_small = S.mini_valid;
+    }
+    if (!use_compiled && !fused_small) gather_periodic(per_lag.p, act, n_act);
 
     if (!reuse) {
         const size_t t_sched = tic(T_SCHED);
         const size_t t_k = tic(T_KERNEL, cur);
-        build_schedule(S, cur, /*solve=*/true, 0, Dl, nullptr);
+        {
+            SchedProbe pr(stream, "init_counts + build");
+            build_schedule(S, cur, /*solve=*/true, 0, Dl, nullptr);
+            if (pr.on) fprintf(stderr, "[sched] level %d: %u active cells, %llu tasks, %u wavefront levels\n", cur, S.n_act,
+                               (unsigned long long)S.n_tasks, S.n_levels);
+        }
         toc(t_k);
         timings.sweep_kernel_launches += 1;
         timings.sweep_kernel_tasks += S.n_tasks;
@@ -921,16 +1035,25 @@ void Sweep::single_sweep(int cur) {
         S.level_off.ensure(S.n_levels + 1);
         CUDA_CHECK(cudaMemcpyAsync(S.level_off.p, level_off_scratch.p, sizeof(uint32_t) * (S.n_levels + 1),
                                    cudaMemcpyDeviceToDevice, stream));
+        SchedProbe pr_keep(stream, "keep level sets");
         if (cache_ok) {
-            size_t bytes = 0;
-            CUDA_CHECK(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, queue_scratch.p, S.tasks.p,
-                                                          (int64_t)S.n_tasks, (int64_t)S.n_levels,
-                                                          S.level_off.p, S.level_off.p + 1, stream));
-            cub_temp.ensure(bytes);
-            CUDA_CHECK(cub::DeviceSegmentedSort::SortKeys(cub_temp.p, bytes, queue_scratch.p, S.tasks.p,
-                                                          (int64_t)S.n_tasks, (int64_t)S.n_levels,
-                                                          S.level_off.p, S.level_off.p + 1, stream));
-            launched(3);
+            // The level sets as the build left them (level by level, arbitrary order inside a level: the gather form does
+            // not care).  Sorting every level by (direction, cell) makes replays walk memory in order; it pays for the
+            // all-cells schedule (built once per grid), not for partial sets, which are rebuilt whenever a level changes
+            // (measured on the ionization-front workload: the segmented sort was most of the rebuild).
+            if (all || stream_env_u32("SSW_SORT_LEVELS", 0)) {
+                size_t bytes = 0;
+                CUDA_CHECK(cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, queue_scratch.p, S.tasks.p,
+                                                              (int64_t)S.n_tasks, (int64_t)S.n_levels,
+                                                              S.level_off.p, S.level_off.p + 1, stream));
+                cub_temp.ensure(bytes);
+                CUDA_CHECK(cub::DeviceSegmentedSort::SortKeys(cub_temp.p, bytes, queue_scratch.p, S.tasks.p,
+                                                              (int64_t)S.n_tasks, (int64_t)S.n_levels,
+                                                              S.level_off.p, S.level_off.p + 1, stream));
+                launched(3);
+            } else {
+                CUDA_CHECK(cudaMemcpyAsync(S.tasks.p, queue_scratch.p, sizeof(uint32_t) * S.n_tasks, cudaMemcpyDeviceToDevice, stream));
+            }
             S.valid = true;
             S.version = levels_version;
         }
@@ -982,6 +1105,9 @@ void Sweep::single_sweep(int cur) {
                                              pcells.p, n_periodic, pidx.p, q.p, num_sms, stream, &stat[SSW_STAT_KERNEL_LAUNCHES],
                                              /*allow_walk=*/true);
                             walked = true;
+                            stat[SSW_STAT_WALK_WINDOW] = S.compiled.window;
+                            stat[SSW_STAT_WALK_NEAR_PERMILLE] =
+                                (uint64_t)(1000.0 * (double)S.compiled.n_near / (double)std::max<uint64_t>(1, S.compiled.n_near + S.compiled.n_far));
                         }
                     } catch (const WalkUnsupported &e) {
                         patch_note += std::string(patch_note.empty() ? "" : "; ") + e.what();
@@ -1026,8 +1152,27 @@ void Sweep::single_sweep(int cur) {
             // partial schedules replay from stored task records; they are (re)built on first use and when the
             // flux state moved into slot order since
             const bool want_mini = !all && S.n_tasks <= (64u << 20);
-            if (want_mini && (!S.mini_valid || S.mini_slot_state != (state != nullptr))) build_mini(S);
-            if (want_mini && S.mini_valid) {
+            if (fused_small) {
+                SmallSweepArgs fs;
+                fs.a = a; fs.m = S.mini_view(); fs.queue = qp; fs.level_off = lo; fs.n_levels = nl;
+                fs.act = act; fs.n_act = n_act; fs.per_lag = per_lag.p; fs.per_new = per_new.p;
+                // photon_rate bookkeeping inside the block only while it is small; else its own (parallel) kernel below
+                const bool photon_inside = (uint64_t)S.n_touch * Dl <= (uint64_t)kSmallPhotonScratch;
+                fs.touch = photon_valid && S.n_touch && photon_inside ? S.touch_list.p : nullptr;
+                fs.n_touch = S.n_touch; fs.photon = photon.p; fs.rate_act = rate_act.p; fs.n_local_dirs = Dl;
+                fs.peers = P.world_size > 1 && peers ? 1 : 0;
+                small_sweep_kernel<<<1, kMiniSmallThreads, 0, stream>>>(fs, pt);
+                if (photon_valid && S.n_touch && !photon_inside) {
+                    photon_patch_kernel<<<S.n_touch, kMaxDirs, 0, stream>>>(grid_view(), state_view(), S.touch_list.p, Dl, photon.p);
+                    launched();
+                }
+            } else if (want_mini && (!S.mini_valid || S.mini_slot_state != (state != nullptr))) {
+                SchedProbe pr(stream, "task records (mini)");
+                build_mini(S);
+            }
+            if (fused_small) {
+                // done above
+            } else if (want_mini && S.mini_valid) {
                 MiniView mv = S.mini_view();
                 if (S.max_level_tasks <= 2048) {
                     mini_replay_small_kernel<<<1, kMiniSmallThreads, 0, stream>>>(a, mv, qp, lo, nl);
@@ -1066,6 +1211,8 @@ void Sweep::single_sweep(int cur) {
         s_rate_finish_kernel<<<cdiv(N, 256), 256, 0, stream>>>(N, C.n_groups, C.n_groups_per, n_periodic, Dl, (double)D, C.acc_cell,
                                                                C.acc_per, pidx.p, src.p, rate_act.p, photon.p);
         photon_valid = true;
+    } else if (fused_small) {
+        // photon_rate bookkeeping, periodic rows and the rate fold ran inside small_sweep_kernel
     } else {
         if (all) {
             photon_valid = false;   // re-evaluated on demand (read_field)
@@ -1090,14 +1237,14 @@ void Sweep::single_sweep(int cur) {
     if (P.world_size > 1 && peers) {
         // peer-mapped exchange: partial rates straight into the owners' receive buffers, chemistry on the owner, new
         // absorption factors straight into every rank's array (peer.cuh)
-        peer_push_rates_kernel<<<cdiv(n_act, 256), 256, 0, stream>>>(pt, act, n_act, rate_act.p, blocks_done.p);
-        launched();
+        if (!fused_small) {               // (the fused small sweep pushed its rates and signalled)
+            peer_push_rates_kernel<<<cdiv(n_act, 256), 256, 0, stream>>>(pt, act, n_act, rate_act.p, blocks_done.p);
+            launched();
+        }
         peer_wait();                      // everybody's partial rates of my cells have arrived
         const uint32_t n_launch = all ? pt.n_own() : n_act;
         if (n_launch) {                   // the kernel's tail signals every rank
-            chemistry_kernel<<<cdiv(n_launch, 128), 128, 0, stream>>>(cell_view(), act, n_launch, nullptr, cp, chem_stats.p,
-                                                                       all ? pt.first() : 0u, peer_chem());
-            launched();
+            launch_chemistry(act, n_launch, nullptr, all ? pt.first() : 0u, cp, peer_chem());
         } else {
             peer_signal_kernel<<<1, 32, 0, stream>>>(pt);
             launched();
@@ -1113,7 +1260,7 @@ void Sweep::single_sweep(int cur) {
         run_collective(SSW_COLL_REDUCE_SCATTER, rate_act.p, n_per);
         double *chunk = chem_pack.p + (size_t)P.rank * kPackFields * n_per;
         if (n_own) {
-            chemistry_kernel<<<cdiv(n_own, 128), 128, 0, stream>>>(cell_view(), nullptr, n_own, rate_act.p + first, cp, chem_stats.p, first, PeerChem{});
+            launch_chemistry(nullptr, n_own, rate_act.p + first, first, cp, PeerChem{});
             chem_pack_kernel<<<cdiv(n_own, 256), 256, 0, stream>>>(cell_view(), first, n_own, n_per, chunk);
             launched(2);
         }
@@ -1122,8 +1269,7 @@ void Sweep::single_sweep(int cur) {
         launched();
     } else {
         maybe_allreduce(rate_act.p, n_act);
-        chemistry_kernel<<<cdiv(n_act, 128), 128, 0, stream>>>(cell_view(), act, n_act, rate_act.p, cp, chem_stats.p, 0u, PeerChem{});
-        launched();
+        launch_chemistry(act, n_act, rate_act.p, 0u, cp, PeerChem{});
     }
     CUDA_CHECK(cudaGetLastError());
     toc(t_chem);
@@ -1192,6 +1338,14 @@ double Sweep::run_sweeps() {
     stat[SSW_STAT_CHEM_FAILURES] = cs.failures;
     stat[SSW_STAT_CHEM_ATTEMPTS] = cs.attempts;
     stat[SSW_STAT_CHEM_MAX_DEPTH] = cs.max_depth;
+    // substepping in this step (more attempts than cell updates): balance the warps of the next step's launches
+    {
+        const uint64_t da = cs.attempts - chem_prev_attempts, dc = cs.cells - chem_prev_cells;
+        chem_prev_attempts = cs.attempts;
+        chem_prev_cells = cs.cells;
+        const uint32_t forced = stream_env_u32("SSW_CHEM_BALANCE", 2);
+        chem_balance = forced < 2 ? forced != 0 : (dc > 0 && (double)da > 1.25 * (double)dc);
+    }
     return elapsed;
 }
 
@@ -1327,6 +1481,13 @@ int ssw_set_allreduce(ssw_handle *h, ssw_allreduce_fn fn, void *ctx) {
     REQUIRE_HANDLE(h);
     h->s.allreduce = fn;
     h->s.allreduce_ctx = ctx;
+    SSW_CATCH
+}
+
+int ssw_set_directions(ssw_handle *h, const double *dirs_xyz) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    h->s.set_directions(dirs_xyz);
     SSW_CATCH
 }
 

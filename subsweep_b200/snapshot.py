@@ -190,3 +190,22 @@ def to_hdf5(directory: Union[str, Path]) -> list:
                     ds.attrs[key] = np.int32(a[key])
         out.append(path)
     return out
+
+
+def remap_from(positions, temperature, ionized_hydrogen_fraction, old_positions, old_temperature,
+               old_ionized_hydrogen_fraction, box_size=None):
+    """``remap_abundances_and_energies_system`` (src/arepo_postprocess/remap.rs:380-429): initialise a run from the last
+    snapshot of an earlier one.  Every particle looks up the old particle nearest to its position (periodic box if
+    ``box_size`` is given) and keeps the larger temperature and the larger ionized fraction (``remap_from``,
+    remap.rs:381-384).  Host-side preprocessing in front of ``Sweep``; returns the new (temperature, fraction)."""
+    from scipy.spatial import cKDTree
+
+    old = np.asarray(old_positions, dtype=np.float64)
+    new = np.asarray(positions, dtype=np.float64)
+    if box_size is not None:
+        old, new = np.mod(old, box_size), np.mod(new, box_size)
+    tree = cKDTree(old, boxsize=box_size)
+    _, idx = tree.query(new)
+    return (np.maximum(np.asarray(temperature, dtype=np.float64), np.asarray(old_temperature, dtype=np.float64)[idx]),
+            np.maximum(np.asarray(ionized_hydrogen_fraction, dtype=np.float64),
+                       np.asarray(old_ionized_hydrogen_fraction, dtype=np.float64)[idx]))

@@ -93,6 +93,25 @@ class SweepParameters:
         return cls.from_dict(yaml.safe_load(text)["sweep"])
 
 
+def rotation_matrix(axis, angle: float) -> np.ndarray:
+    """get_rotation_matrix (src/sweep/direction/mod.rs:113-134): axis-angle (Rodrigues) rotation."""
+    x, y, z = axis
+    c, s = np.cos(angle), np.sin(angle)
+    return np.array([
+        [c + x * x * (1.0 - c), x * y * (1.0 - c) - z * s, x * z * (1.0 - c) + y * s],
+        [y * x * (1.0 - c) + z * s, c + y * y * (1.0 - c), y * z * (1.0 - c) - x * s],
+        [z * x * (1.0 - c) - y * s, z * y * (1.0 - c) + x * s, c + z * z * (1.0 - c)]])
+
+
+def random_rotation_matrix(rng: np.random.Generator) -> np.ndarray:
+    """get_random_rotation_matrix (:136-148): uniform axis on the sphere, uniform angle -- the same construction, drawn
+    from a numpy Generator (the reference seeds a Rust StdRng with 1337, whose stream cannot be reproduced here)."""
+    phi = rng.uniform(0.0, 2.0 * np.pi)
+    theta = np.arccos(2.0 * rng.uniform(0.0, 1.0) - 1.0)
+    axis = (np.cos(phi) * np.sin(theta), np.sin(phi) * np.sin(theta), np.cos(theta))
+    return rotation_matrix(axis, rng.uniform(0.0, 2.0 * np.pi))
+
+
 AllReduce = Callable[[int, int, Optional[int]], None]   # (pointer, n_doubles, stream) -> in-place sum
 # (op, pointer, n_doubles_per_rank, stream): in-place reduce-scatter (op 1) / all-gather (op 2) over world_size chunks
 Collectives = Callable[[int, int, int, Optional[int]], None]
@@ -137,8 +156,8 @@ class Sweep:
                  temperature, source, scale_factor: float = 1.0, device_id: int = 0, rank: int = 0,
                  world_size: int = 1, allreduce: Optional[AllReduce] = None, flags: int = 0, lib=None,
                  positions="grid", collectives: Optional[Collectives] = None):
-        if parameters.rotate_directions:
-            raise NotImplementedError("rotate_directions is not supported yet (DESIGN.md, out of scope)")
+        if parameters.rotate_directions and world_size > 1:
+            raise NotImplementedError("rotate_directions is not available under direction sharding")
         self.lib = lib if lib is not None else capi.load()
         self.parameters = parameters
         self.grid = grid
@@ -270,6 +289,15 @@ class Sweep:
     def update_timestep_levels(self) -> None:
         self._check(self.lib.ssw_update_timestep_levels(self._h))
 
+    def set_directions(self, xyz) -> None:
+        """rotate_directions_system (src/sweep/direction/mod.rs:158-174): continue with another direction set of the same
+        size; the flux state follows the best aligned old direction (ssw_set_directions)."""
+        v = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        if v.shape != self.directions.xyz.shape:
+            raise ValueError("the new direction set must have the same size")
+        self._check(self.lib.ssw_set_directions(self._h, capi.dptr(v)))
+        self.directions = Directions(v)
+
     def set_inputs(self, density=None, source=None) -> None:
         d = None if density is None else np.ascontiguousarray(density, dtype=np.float64)
         s = None if source is None else np.ascontiguousarray(source, dtype=np.float64)
@@ -378,6 +406,7 @@ class SweepPlugin:
     allreduce: Optional[AllReduce] = None
     collectives: Optional[Collectives] = None
     solver: Optional[Sweep] = field(default=None, init=False)
+    directions_rng: np.random.Generator = field(default_factory=lambda: np.random.default_rng(1337), init=False)  # DIRECTIONS_RNG_SEED
     is_first_time: bool = field(default=True, init=False)
     simulation_time: float = field(default=0.0, init=False)
 
@@ -399,6 +428,9 @@ class SweepPlugin:
             self.is_first_time = False
             return
         s = self.solver
+        if self.parameters.rotate_directions:   # rotate_directions_system runs in front of the sweep (mod.rs:143-149)
+            m = random_rotation_matrix(self.directions_rng)
+            s.set_directions(s.directions.xyz @ m.T)
         self.simulation_time += s.run_sweeps()
         s.read("ionized_hydrogen_fraction", components["ionized_hydrogen_fraction"])
         s.read("temperature", components["temperature"])

@@ -245,3 +245,36 @@ def test_failing_collective_hooks_return_an_error_code(capsys):
     assert "allreduce hook failed" in err and "collective hook failed" in err
     ok = allreduce_trampoline(lambda *a: None)
     assert ok(None, 8, 4, None) == 0
+
+
+def test_random_rotation_is_a_rotation():
+    """get_random_rotation_matrix (src/sweep/direction/mod.rs:113-148) in the Python mirror."""
+    from subsweep_b200.sweep import random_rotation_matrix, rotation_matrix
+    m = random_rotation_matrix(np.random.default_rng(1337))
+    assert np.allclose(m @ m.T, np.eye(3), atol=1e-14) and abs(np.linalg.det(m) - 1.0) < 1e-14
+    z90 = rotation_matrix((0.0, 0.0, 1.0), np.pi / 2)
+    assert np.allclose(z90 @ np.array([1.0, 0.0, 0.0]), [0.0, 1.0, 0.0], atol=1e-15)
+
+
+def test_remap_from_takes_the_nearest_old_particle_and_the_larger_value():
+    """remap_abundances_and_energies_system (src/arepo_postprocess/remap.rs:380-429)."""
+    from subsweep_b200.snapshot import remap_from
+    old_pos = np.array([[0.1, 0.1, 0.1], [0.9, 0.9, 0.9], [0.5, 0.5, 0.5]])
+    new_pos = np.array([[0.12, 0.1, 0.1], [0.52, 0.5, 0.49], [0.02, 0.98, 0.95]])
+    T, x = remap_from(new_pos, [100.0, 5e4, 100.0], [1e-10, 0.9, 1e-10], old_pos, [2e4, 100.0, 1e4], [0.5, 1e-10, 0.3], box_size=1.0)
+    assert T.tolist() == [2e4, 5e4, 100.0] and x.tolist() == [0.5, 0.9, 1e-10]       # third: nearest through the wrap is old #1
+    T2, _ = remap_from(new_pos, [100.0] * 3, [1e-10] * 3, old_pos, [2e4, 100.0, 1e4], [0.5, 1e-10, 0.3])
+    assert T2.tolist() == [2e4, 1e4, 1e4]                                             # no wrap: old #2 is nearer
+
+
+def test_rust_sys_crate_declares_every_symbol():
+    """crates/subsweep_b200_sys/src/lib.rs is a transcription of the header: same functions, same enum values."""
+    header = (ROOT / "include" / "subsweep_b200.h").read_text()
+    crate = (ROOT / "crates" / "subsweep_b200_sys" / "src" / "lib.rs").read_text()
+    declared = set(re.findall(r"\b(ssw_[a-z_0-9]+)\s*\(", header)) - {"ssw_allreduce_fn"}
+    bound = set(re.findall(r"pub fn (ssw_[a-z_0-9]+)\s*\(", crate))
+    assert declared == bound, declared ^ bound
+    for name, value in re.findall(r"SSW_F_([A-Z_]+) = (\d+)", header):
+        assert re.search(rf"\b{name} = {value},", crate), name
+    for name, value in re.findall(r"SSW_STAT_([A-Z_]+) = (\d+)", header):
+        assert re.search(rf"\b{name} = {value},", crate), name
