@@ -288,6 +288,18 @@ def pinned(n: int) -> np.ndarray:
     return torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
 
 
+def all_cells_form(sweep) -> str:
+    """Which compiled form the all-cells sweep runs in and the kernel that carries it."""
+    if sweep.stat("patch_macro_tiles"):
+        return "patch_sweep_kernel (macro-tile dataflow, %d macro-tiles in %d dependent levels)" % (
+            sweep.stat("patch_macro_tiles"), sweep.stat("patch_levels"))
+    why = sweep.patch_note() or "patch form off"
+    if sweep.stat("walk_window"):
+        return "walk_kernel (one block per direction, %d-slot shared-memory window, %.1f %% of the upwind entries read from it; %s)" % (
+            sweep.stat("walk_window"), sweep.stat("walk_near_permille") / 10.0, why)
+    return "sweep_stream_kernel (level-barrier stream; %s)" % why
+
+
 def run_b200(args) -> None:
     import torch
     import torch.distributed as dist
@@ -378,7 +390,7 @@ def run_b200(args) -> None:
                               "level_counts": [int(v) for v in sweep.level_counts()],
                               "chem_attempts": sweep.stat("chem_attempts"), "chem_cells": sweep.stat("chem_cells"),
                               "chem_max_depth": sweep.stat("chem_max_depth"), "schedule_builds": sweep.stat("schedule_builds"),
-                              "all_cells_form": "patch dataflow" if sweep.stat("patch_macro_tiles") else "level-barrier stream (" + (sweep.patch_note() or "patch form off") + ")",
+                              "all_cells_form": all_cells_form(sweep),
                               "macro_tiles": sweep.stat("patch_macro_tiles"), "patch_levels": sweep.stat("patch_levels"),
                               "patch_phases": sweep.stat("patch_phases"),
                               "mean_xhii": float(sweep.read("ionized_hydrogen_fraction").mean()),
@@ -450,8 +462,7 @@ def run_b200(args) -> None:
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": traffic_source,
         "algorithmic_bytes_per_launch": b_alg * k_tasks / k_launches,
-        "kernel": ("patch_sweep_kernel (macro-tile dataflow, %d macro-tiles in %d dependent levels)" % (sweep.stat("patch_macro_tiles"), sweep.stat("patch_levels"))
-                   if sweep.stat("patch_macro_tiles") else "sweep_stream_kernel (level-barrier stream)") + " of the all-cells single sweep (timestep level %d)" % lvl,
+        "kernel": all_cells_form(sweep) + " of the all-cells single sweep (timestep level %d)" % lvl,
         "algorithmic_bytes_per_update": b_alg, "mean_upwind_faces": f_up,
         "updates_per_launch": k_tasks / k_launches, "ms_per_launch": k_ms / k_launches, "peak_source": peak_kind,
     }

@@ -26,6 +26,7 @@ STATS = {
     "tasks_solved": 0, "single_sweeps": 1, "chem_cells": 2, "chem_failures": 3, "schedule_builds": 4,
     "schedule_replays": 5, "kernel_launches": 6, "wavefront_levels": 7, "chem_attempts": 8,
     "chem_max_depth": 9, "patch_macro_tiles": 10, "patch_levels": 11, "patch_phases": 12,
+    "walk_window": 13, "walk_near_permille": 14,
 }
 
 c_double_p = C.POINTER(C.c_double)
