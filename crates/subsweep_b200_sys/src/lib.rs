@@ -178,6 +178,7 @@ extern "C" {
     pub fn ssw_get_stat(h: *mut ssw_handle, which: ssw_stat, out: *mut u64) -> c_int;
     pub fn ssw_get_timings(h: *mut ssw_handle, out: *mut ssw_timings) -> c_int;
     pub fn ssw_reset_timings(h: *mut ssw_handle) -> c_int;
+    pub fn ssw_set_timing_level(h: *mut ssw_handle, level: i32) -> c_int;
 
     pub fn ssw_direction_shard(n_dirs: i32, world_size: i32, rank: i32, begin: *mut i32, end: *mut i32) -> c_int;
     pub fn ssw_patch_lattice(xyz: *const f64, n_cells: u64, target_cells: i32, patch_of: *mut u32) -> i32;

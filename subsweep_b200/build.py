@@ -10,8 +10,7 @@ ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIB = ROOT / "lib" / "libsubsweep_b200.so"
 SOURCES = [CSRC / "sweep.cu"]
-HEADERS = [CSRC / "kernels.cuh", CSRC / "stream.cuh", CSRC / "patch.cuh", CSRC / "chemistry.cuh",
-           ROOT.parent / "include" / "subsweep_b200.h"]
+HEADERS = sorted(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "subsweep_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

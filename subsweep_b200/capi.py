@@ -113,6 +113,7 @@ SYMBOLS = {
     "ssw_get_stat": (C.c_int, [H, C.c_int, C.POINTER(C.c_uint64)]),
     "ssw_get_timings": (C.c_int, [H, C.POINTER(Timings)]),
     "ssw_reset_timings": (C.c_int, [H]),
+    "ssw_set_timing_level": (C.c_int, [H, C.c_int32]),
     "ssw_direction_shard": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ssw_patch_lattice": (C.c_int32, [c_double_p, C.c_uint64, C.c_int32, C.POINTER(C.c_uint32)]),
     "ssw_direction_groups": (C.c_int32, [c_double_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),

@@ -87,7 +87,8 @@ struct __align__(16) PHdr {
     uint16_t kind;     // 0 tile, 1 head
     uint16_t n;        // tile: slots; head: upwind macro-tiles to wait for
     uint16_t a16;      // tile: entries; head: cells of the patch
-    uint16_t b16;      // tile: bit 0 = last tile of the macro-tile; head: direction group | directions in the group << 10
+    uint16_t b16;      // tile: bit 0 = last tile of the macro-tile, bits 1-3 = K if every slot has exactly K Local entries and
+                       // no periodic ones (else 0); head: direction group | directions in the group << 10
     uint32_t c32;      // tile: first slot of the tile inside the macro-tile; head: external entries
     uint32_t next_off16, next_bytes;   // packet that goes into this ring stage next (bytes = 0: none)
     uint32_t gslot0;   // head: first global slot of the macro-tile; tile: idx offset | lcell offset << 16 (16-B units)
@@ -447,6 +448,11 @@ p_fill_kernel(PFillArgs a) {
         const uint32_t used = n + 1u, pad_info = (align16(4u * used) - 4u * used) / 4u;
         if (tid < pad_info) info[used + tid] = 0u;
     }
+    // A tile whose slots all have the same number K <= 4 of Local upwind entries and no periodic ones (every interior
+    // tile of a Cartesian grid: K = 3) is flagged in its header: the kernel then indexes the entries as K * slot and
+    // never reads the info words.
+    __shared__ uint32_t s_deg0;
+    uint32_t my_deg = 0, my_per = 0;
     if (tid < n) {
         const uint32_t s = slot0 + tid;
         const uint32_t k = a.k32[s];
@@ -489,12 +495,17 @@ p_fill_kernel(PFillArgs a) {
             }
         }
         info[tid] = e0 | (min(n_per, 255u) << 16);
+        my_deg = e - e0;
+        my_per = n_per;
+        if (tid == 0) s_deg0 = my_deg;
     }
     __syncthreads();
+    const bool uniform = __syncthreads_and(tid >= n || (my_per == 0u && my_deg == s_deg0)) != 0;
     if (tid == 0) {
         info[n] = E;
         h.kind = 0; h.n = (uint16_t)n; h.a16 = (uint16_t)E;
-        h.b16 = (uint16_t)((d.flags & kPLast) ? 1u : 0u);
+        const uint32_t K = uniform && s_deg0 >= 1u && s_deg0 <= 4u ? s_deg0 : 0u;
+        h.b16 = (uint16_t)(((d.flags & kPLast) ? 1u : 0u) | (K << 1));
         h.c32 = slot0 - mt0;
         h.gslot0 = (L.idx >> 4) | ((L.lcell >> 4) << 16);   // tile packets: section offsets in 16-B units
         h.n_slots = L.info >> 4;
@@ -568,6 +579,13 @@ struct PatchArgs {
     unsigned long long *prof; // optional per-block cycle counters, 10 per block (SSW_STREAM_PROFILE)
 };
 
+// One-warp blocks (THREADS == 32) separate the sub-levels of a macro-tile with a warp barrier instead of a block barrier:
+// nothing on the dependent chain of a direction shard waits for another warp.
+template <int THREADS>
+__device__ __forceinline__ void patch_block_sync() {
+    if constexpr (THREADS == 32) __syncwarp(); else __syncthreads();
+}
+
 template <int THREADS, int MIN_BLOCKS, bool PROFILE>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 patch_sweep_kernel(PatchArgs a) {
@@ -593,7 +611,7 @@ patch_sweep_kernel(PatchArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         policy = policy_evict_first();
     }
-    __syncthreads();
+    patch_block_sync<THREADS>();
     if (tid == THREADS - 32) {
         const PDesc *tab = a.ptab + a.tab_off[blockIdx.x];
         const uint32_t pre = min(stages, n_my);
@@ -626,7 +644,37 @@ patch_sweep_kernel(PatchArgs a) {
             const uint32_t *const cells = reinterpret_cast<const uint32_t *>(pkt + L.cells);
             cellid_buf ^= 1u;
             s_cellid = reinterpret_cast<uint32_t *>(smem + SL.cellid) + cellid_buf * cellid_stride;
-            if (tid < 32u) {
+            if constexpr (THREADS == 32) {
+                // one warp: stage first (the cell records do not depend on the upwind macro-tiles; the loads of a round
+                // are independent), then poll
+                for (uint32_t i0 = 0; i0 < n_cells; i0 += 8u * 32u) {
+                    uint32_t cc[8];
+                    double2 rr[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t i = i0 + (uint32_t)j * 32u + tid;
+                        cc[j] = i < n_cells ? cells[i] : 0u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rr[j] = __ldg(a.cellrec + cc[j]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t i = i0 + (uint32_t)j * 32u + tid;
+                        if (i < n_cells) { s_cellid[i] = cc[j]; s_rec[i] = rr[j]; }
+                    }
+                }
+                if (a.accumulate)
+                    for (uint32_t i = tid; i < n_cells * kdg; i += 32u) s_inc[i] = 0.0;
+                if (tid < n_dep) {
+                    if (PROFILE && tid == 0) tp = clock64();
+                    for (uint32_t i = tid; i < n_dep; i += 32u) {
+                        const unsigned int *flag = a.mt_flag + dep[i];
+                        while (ld_relaxed_gpu(flag) != a.epoch) __nanosleep(a.poll_ns);
+                    }
+                    fence_acq_rel_gpu();
+                    if (PROFILE && tid == 0) t_poll += clock64() - tp;
+                }
+            } else if (tid < 32u) {
                 // warp 0 only polls: the flag round trips start at once and run beside the staging of the other warps
                 if (tid < n_dep) {
                     if (PROFILE && tid == 0) tp = clock64();
@@ -647,7 +695,7 @@ patch_sweep_kernel(PatchArgs a) {
                 if (a.accumulate)   // ragged macro-tile: not every (cell, direction) of the patch has a task here
                     for (uint32_t i = tid - 32u; i < n_cells * kdg; i += THREADS - 32u) s_inc[i] = 0.0;
             }
-            __syncthreads();
+            patch_block_sync<THREADS>();
             double *const vx = val + n_slots;
             for (uint32_t i = tid; i < n_ext; i += 8u * THREADS) {   // eight independent gathers in flight per thread
                 double v[8];
@@ -662,7 +710,7 @@ patch_sweep_kernel(PatchArgs a) {
                     if (ij < n_ext) vx[ij] = v[j];
                 }
             }
-            __syncthreads();   // external values visible; every thread is done with the stage
+            patch_block_sync<THREADS>();   // external values visible; every thread is done with the stage
             if (tid == THREADS - 32 && h.next_bytes) {
                 mbar_expect_tx(smem_u32(full + stage), h.next_bytes);
                 tma_bulk_load(smem_u32(pkt), stream + (size_t)h.next_off16 * 16u, h.next_bytes, smem_u32(full + stage), policy);
@@ -674,18 +722,33 @@ patch_sweep_kernel(PatchArgs a) {
             const uint16_t *const idx = reinterpret_cast<const uint16_t *>(pkt + ((h.gslot0 & 0xffffu) << 4));
             const uint16_t *const lcell = reinterpret_cast<const uint16_t *>(pkt + ((h.gslot0 >> 16) << 4));
             const uint32_t *const info = reinterpret_cast<const uint32_t *>(pkt + (h.n_slots << 4));
+            const uint32_t uniform_k = (h.b16 >> 1) & 7u;
             if (tid < n) {   // (warps beyond the tile's slots only keep the barrier)
                 const uint32_t lcj = lcell[tid];   // patch-local cell | index of the direction inside its group << 10
-                const uint32_t inf = info[tid];
-                const uint32_t e1 = info[tid + 1] & 0xffffu;
                 const uint32_t lc = lcj & 0x3ffu;
                 const double2 rec = s_rec[lc];
-                uint32_t e = inf & 0xffffu;
-                const uint32_t em = e1 - ((inf >> 16) & 0xffu);
                 double in_loc = 0.0, in_per = 0.0;
                 // product and sum rounded separately, Local faces in face order, then the periodic ones: the
-                // arithmetic of stream.cuh bit for bit.  Four entries per round: their loads are independent,
-                // only the additions form a chain.
+                // arithmetic of stream.cuh bit for bit.
+                if (uniform_k == 3u) {
+                    // every slot of the tile has exactly three Local entries (interior of a Cartesian grid): no info
+                    // words, no predicates, all six loads independent
+                    const uint32_t e = 3u * tid;
+                    const uint32_t i0 = idx[e], i1 = idx[e + 1u], i2 = idx[e + 2u];
+                    const double w0 = w[e], w1 = w[e + 1u], w2 = w[e + 2u];
+                    const double v0 = val[i0], v1 = val[i1], v2 = val[i2];
+                    in_loc = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(v0, w0)), __dmul_rn(v1, w1)), __dmul_rn(v2, w2));
+                } else if (uniform_k) {
+                    uint32_t e = uniform_k * tid;
+                    const uint32_t em = e + uniform_k;
+#pragma unroll 1
+                    for (; e < em; ++e) in_loc = __dadd_rn(in_loc, __dmul_rn(val[idx[e]], w[e]));
+                } else {
+                const uint32_t inf = info[tid];
+                const uint32_t e1 = info[tid + 1] & 0xffffu;
+                uint32_t e = inf & 0xffffu;
+                const uint32_t em = e1 - ((inf >> 16) & 0xffu);
+                // Four entries per round: their loads are independent, only the additions form a chain.
 #pragma unroll 1
                 for (; e < em; e += 4u) {
                     uint32_t vi[4];
@@ -704,6 +767,7 @@ patch_sweep_kernel(PatchArgs a) {
                 }
 #pragma unroll 1
                 for (uint32_t ep = em; ep < e1; ++ep) in_per = __dadd_rn(in_per, __dmul_rn(val[idx[ep]], w[ep]));
+                }
                 const double total = (in_loc + rec.y) + in_per;         // site.rs:49-56
                 // HydrogenOnly::get_outgoing_rate, hydrogen_only/mod.rs:81-87
                 const double out = (total < threshold) ? 0.0 : total * rec.x;
@@ -712,12 +776,14 @@ patch_sweep_kernel(PatchArgs a) {
                 s_inc[lc * kdg + (lcj >> 10)] = in_loc;                 // incoming_total_rate[d], summed per cell when the macro-tile is done
             }
             if (PROFILE && tid == 0) { const long long t = clock64(); t_cmp += t - tq; tq = t; }
-            __syncthreads();   // this sub-level's rates are visible; every thread is done with the stage
+            patch_block_sync<THREADS>();   // this sub-level's rates are visible; every thread is done with the stage
             if (PROFILE && tid == 0) { const long long t = clock64(); t_bar += t - tq; tq = t; }
             // the ring stage was only read (generic proxy), never written: no proxy fence before the refill
-            if (tid == THREADS - 32 && h.next_bytes) {
-                mbar_expect_tx(smem_u32(full + stage), h.next_bytes);
-                tma_bulk_load(smem_u32(pkt), stream + (size_t)h.next_off16 * 16u, h.next_bytes, smem_u32(full + stage), policy);
+            if ((tid >> 5) == (uint32_t)(THREADS / 32 - 1)) {   // warp-uniform: the other warps branch around the issue code
+                if (tid == THREADS - 32 && h.next_bytes) {
+                    mbar_expect_tx(smem_u32(full + stage), h.next_bytes);
+                    tma_bulk_load(smem_u32(pkt), stream + (size_t)h.next_off16 * 16u, h.next_bytes, smem_u32(full + stage), policy);
+                }
             }
             if (h.b16 & 1u) {
                 // ---- macro-tile done.  Every outgoing rate of the macro-tile was stored before the barrier above, so the
@@ -743,7 +809,7 @@ patch_sweep_kernel(PatchArgs a) {
                         double *const dst = acc + s_cellid[i];
                         __stcg(dst, __ldcg(dst) + sum);
                     }
-                    __syncthreads();
+                    patch_block_sync<THREADS>();
                     if (tid == 0) st_release_gpu(a.mt_flag + rank, a.epoch);
                 }
                 // no barrier: the next head fills the other s_cellid buffer, and two barriers separate it from the
@@ -768,6 +834,7 @@ patch_sweep_kernel(PatchArgs a) {
 typedef void (*PatchKernel)(PatchArgs);
 inline PatchKernel patch_kernel_for(uint32_t threads, bool profile) {
     // minimum blocks per SM chosen so that the register file never limits residency below 1024 threads (<= 64 registers)
+    if (threads == 32) return profile ? patch_sweep_kernel<32, 16, true> : patch_sweep_kernel<32, 16, false>;
     if (profile) return threads == 64 ? patch_sweep_kernel<64, 16, true> : threads == 128 ? patch_sweep_kernel<128, 8, true> : patch_sweep_kernel<256, 4, true>;
     return threads == 64 ? patch_sweep_kernel<64, 16, false> : threads == 128 ? patch_sweep_kernel<128, 8, false> : patch_sweep_kernel<256, 4, false>;
 }
@@ -878,7 +945,7 @@ inline void compile_patch_schedule(Compiled &C, const GridView &g, const PatchGr
     if (n_tasks != (uint64_t)g.n_cells * (uint64_t)n_local_dirs) throw PatchUnsupported("not an all-cells schedule");
     const uint32_t n = (uint32_t)n_tasks, n_dl = (uint32_t)n_local_dirs, N = g.n_cells, P = pg.n_patches;
     const uint32_t threads_env = env_u32("SSW_PATCH_THREADS", 128);
-    const uint32_t threads = threads_env == 256 ? 256u : (threads_env == 64 ? 64u : 128u);
+    const uint32_t threads = threads_env == 256 ? 256u : (threads_env == 64 ? 64u : (threads_env == 32 ? 32u : 128u));
     const uint32_t kd_default = n_dl <= 24 ? 3u : 11u;   // many directions: one group per octant (10-11 of the 84)
     const uint32_t kd = std::max<uint32_t>(1u, std::min<uint32_t>(env_u32("SSW_PATCH_KD", kd_default), 32u));
     const uint32_t want_stages = std::max<uint32_t>(2u, std::min<uint32_t>(env_u32("SSW_PATCH_STAGES", 3), kMaxStages));

@@ -669,26 +669,21 @@ sweep_stream_kernel(StreamArgs a) {
             if (!epilogue) rec = __ldg(a.cellrec + c);
         }
         if (PROFILE && SOLO && tid == 0) tp = clock64();
-        // phase 1: four independent gathers per thread and round
-        for (uint32_t i = tid; i < E; i += 4u * THREADS) {
-            const uint32_t i1 = i + THREADS, i2 = i + 2u * THREADS, i3 = i + 3u * THREADS;
-            const bool p1 = i1 < E, p2 = i2 < E, p3 = i3 < E;
-            double v0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-            if (SOLO) {   // only this block (this SM) ever stores the slots it gathers: L1 is coherent for them
-                v0 = out_slot[es[i]];
-                if (p1) v1 = out_slot[es[i1]];
-                if (p2) v2 = out_slot[es[i2]];
-                if (p3) v3 = out_slot[es[i3]];
-            } else {
-                v0 = __ldcg(out_slot + es[i]);
-                if (p1) v1 = __ldcg(out_slot + es[i1]);
-                if (p2) v2 = __ldcg(out_slot + es[i2]);
-                if (p3) v3 = __ldcg(out_slot + es[i3]);
+        // phase 1: eight independent gathers per thread and round (an unstructured tile holds ~8 entries per slot: one
+        // L2 round trip for the whole tile instead of two)
+        for (uint32_t i = tid; i < E; i += 8u * THREADS) {
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t ij = i + (uint32_t)j * THREADS;
+                v[j] = 0.0;
+                if (ij < E) v[j] = SOLO ? out_slot[es[ij]] : __ldcg(out_slot + es[ij]);   // SOLO: the SM's own stores, L1 is coherent
             }
-            prod[i] = v0 * prod[i];
-            if (p1) prod[i1] = v1 * prod[i1];
-            if (p2) prod[i2] = v2 * prod[i2];
-            if (p3) prod[i3] = v3 * prod[i3];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t ij = i + (uint32_t)j * THREADS;
+                if (ij < E) prod[ij] = v[j] * prod[ij];
+            }
         }
         __syncthreads();
         if (PROFILE && SOLO && tid == 0) { const long long now = clock64(); t_bar += now - tp; tp = now; }
@@ -698,6 +693,12 @@ sweep_stream_kernel(StreamArgs a) {
             uint32_t e = inf & 0xffffu;
             const uint32_t em = e1 - ((inf >> 16) & 0xffu);
             double in_loc = 0.0, in_per = 0.0;
+            // same left-to-right order as one addition per iteration; four loads in flight per round
+#pragma unroll 1
+            for (; e + 4u <= em; e += 4u) {
+                const double p0 = prod[e], p1 = prod[e + 1], p2 = prod[e + 2], p3 = prod[e + 3];
+                in_loc = (((in_loc + p0) + p1) + p2) + p3;
+            }
 #pragma unroll 1
             for (; e < em; ++e) in_loc += prod[e];
 #pragma unroll 1

@@ -251,13 +251,23 @@ struct Sweep {
         CUDA_CHECK(cudaEventCreate(&e));
         return e;
     }
+    // Timing level: 0 = the step and the sweep kernels of the largest active sets only (what a production host and the
+    // roofline of bench.py need: four event records per step), 1 = every phase of every single sweep (the breakdown
+    // ssw_get_timings reports; ~10 event records per single sweep, which cost a direction shard with its microsecond
+    // sub-level sweeps a measurable share of the step).  ssw_set_timing_level / SSW_TIMERS.
+    int timing_level = 1;
+    static constexpr size_t kNoTimer = ~(size_t)0;
     size_t tic(int cat, int lvl = -1) {
+        if (timing_level == 0 && !(cat == T_STEP || (cat == T_KERNEL && lvl == lowest_allowed))) return kNoTimer;
         Pending p{get_event(), get_event(), cat, lvl};
         CUDA_CHECK(cudaEventRecord(p.a, stream));
         pending.push_back(p);
         return pending.size() - 1;
     }
-    void toc(size_t id) { CUDA_CHECK(cudaEventRecord(pending[id].b, stream)); }
+    void toc(size_t id) {
+        if (id == kNoTimer) return;
+        CUDA_CHECK(cudaEventRecord(pending[id].b, stream));
+    }
     void resolve_timers() {
         CUDA_CHECK(cudaStreamSynchronize(stream));
         for (auto &p : pending) {
@@ -525,6 +535,7 @@ void Sweep::create(const ssw_params *p, const ssw_grid *g, const double *density
     blocks_done.alloc(1); blocks_done.zero(stream);
     chem_stats.alloc(1); chem_stats.zero(stream);
     last_attempts.alloc(N); last_attempts.zero(stream);
+    timing_level = (int)std::min<uint32_t>(1u, stream_env_u32("SSW_TIMERS", 1));
     CUDA_CHECK(cudaStreamSynchronize(stream));  // host vectors go out of scope
 
     bind();
@@ -964,7 +975,9 @@ void Sweep::launch_chemistry(const uint32_t *act, uint32_t n, const double *rate
         launched(3);
         order = order_vals_out.p;
     }
-    chemistry_kernel<<<cdiv(n, 128), 128, 0, stream>>>(cell_view(), act, n, rate, cp, chem_stats.p, first_cell, pc, order,
+    // one warp per block: a finished warp frees its registers at once (the kernel holds no shared memory and has no
+    // block-level phase)
+    chemistry_kernel<<<cdiv(n, kChemThreads), kChemThreads, 0, stream>>>(cell_view(), act, n, rate, cp, chem_stats.p, first_cell, pc, order,
                                                        last_attempts.p);
     launched();
 }
@@ -1003,9 +1016,12 @@ void Sweep::single_sweep(int cur) {
     // A small active set whose level sets are cached runs as ONE launch (small.cuh): lagged periodic rows, replay,
     // photon_rate bookkeeping, new periodic rows, rate fold and -- under peer-mapped sharding, where it is the default --
     // the hand-over of the partial rates to their owners.  (On one GPU the chain of small kernels is as fast: measured.)
+    // One block does all of it, so only while the set holds few (cell, direction) rows: measured with 64 active cells,
+    // 10 and 21 local directions (8 and 4 ranks) are on par with the separate kernels, 42 (2 ranks) cost 0.74 ms per
+    // step against 0.28 ms.
     bool fused_small = false;
     if (reuse && !all && !use_compiled && S.n_tasks > 0 && S.n_tasks <= (64u << 20) && S.max_level_tasks <= 2048 &&
-        (uint64_t)n_act * Dl <= 65536 && (uint64_t)S.n_touch * Dl <= 262144 &&
+        (uint64_t)n_act * Dl <= stream_env_u32("SSW_FUSED_SMALL_ROWS", 1536) && (uint64_t)S.n_touch * Dl <= 262144 &&
         (P.world_size == 1 || peers) && stream_env_u32("SSW_FUSED_SMALL", peers ? 1 : 0)) {
         if (!S.mini_valid || S.mini_slot_state != (state != nullptr)) {
             const size_t t_sched = tic(T_SCHED);
@@ -1788,6 +1804,14 @@ int ssw_reset_timings(ssw_handle *h) {
     SSW_TRY
     REQUIRE_HANDLE(h);
     std::memset(&h->s.timings, 0, sizeof(ssw_timings));
+    SSW_CATCH
+}
+
+int ssw_set_timing_level(ssw_handle *h, int32_t level) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    if (level < 0 || level > 1) ssw::fail(SSW_E_INVALID, "timing level %d (0 or 1)", level);
+    h->s.timing_level = level;
     SSW_CATCH
 }
 

@@ -389,6 +389,10 @@ class Sweep:
     def reset_timings(self) -> None:
         self._check(self.lib.ssw_reset_timings(self._h))
 
+    def set_timing_level(self, level: int) -> None:
+        """0: whole steps and the all-cells sweep kernel only; 1: every phase of every single sweep (default)."""
+        self._check(self.lib.ssw_set_timing_level(self._h, int(level)))
+
 
 # ---------------------------------------------------------------------------------------------
 # the two bevy systems of SweepPlugin, on a dict of per-particle component arrays

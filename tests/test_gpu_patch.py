@@ -52,6 +52,22 @@ def test_patch_form_matches_stream_form_on_cartesian_grids(cuda_lib, monkeypatch
         assert_close(a[k], b[k], 1e-12, floor=1e-9 * max(np.nanmax(np.abs(b[k])), 1e-300), what=k)
 
 
+@pytest.mark.parametrize("threads,kd", [(32, 1), (32, 3), (64, 2), (256, 11)])
+def test_patch_kernel_variants_are_bit_identical(cuda_lib, monkeypatch, threads, kd):
+    """Block size and direction-group width of the patch kernel are tunables (SSW_PATCH_THREADS / SSW_PATCH_KD; 32 threads:
+    one warp per macro-tile, warp barriers only).  Per task the arithmetic does not depend on them."""
+    params, g, f = make_problem("cartesian", 12, True, n_dirs=84, n_levels=1)
+    monkeypatch.setenv("SSW_PATCH_CELLS", "64")
+    a = run(params, g, f, 0, 2)
+    monkeypatch.setenv("SSW_PATCH_THREADS", str(threads))
+    monkeypatch.setenv("SSW_PATCH_KD", str(kd))
+    b = run(params, g, f, 0, 2)
+    assert a["macro_tiles"] > 0 and b["macro_tiles"] > 0 and b["note"] == "", b["note"]
+    assert np.array_equal(a["outgoing"], b["outgoing"])
+    for k in FIELDS + ("incoming", "periodic"):
+        assert_close(a[k], b[k], 1e-12, floor=1e-9 * max(np.nanmax(np.abs(b[k])), 1e-300), what=k)
+
+
 @pytest.mark.parametrize("kind,n,periodic", [("cartesian", 12, True), ("cartesian", 11, False), ("voronoi", 9, True),
                                              ("voronoi", 9, False), ("jittered", 8, True)])
 def test_patch_default_against_oracle_with_timestep_levels(cuda_lib, monkeypatch, kind, n, periodic):

@@ -101,3 +101,23 @@ def test_walk_form_matches_stream_form(cuda_lib, monkeypatch, kind, n, periodic,
     for k, v in res["0"].items():
         if k != "levels":
             assert_close(res["1"][k], v, 1e-11, floor=1e-7 * np.nanmax(np.abs(v)), what=k)
+
+
+def test_timing_level_zero_times_steps_and_all_cells_kernels_only(cuda_lib):
+    """ssw_set_timing_level(0): no per-phase event records; the step and the all-cells sweep kernel are still timed, and
+    the results do not depend on the level."""
+    params, g, f = make_problem("cartesian", 10, True, n_dirs=21, n_levels=2, max_timestep_myr=0.25)
+    a, b = Sweep(params, g, **f), Sweep(params, g, **f)
+    b.set_timing_level(0)
+    for _ in range(4):
+        a.run_sweeps()
+        b.run_sweeps()
+    ta, tb = a.timings(), b.timings()
+    assert ta["sweep_ms"] > 0 and ta["chemistry_ms"] > 0 and ta["step_ms"] > 0
+    assert tb["sweep_ms"] == 0 and tb["chemistry_ms"] == 0 and tb["update_levels_ms"] == 0
+    assert tb["step_ms"] > 0 and tb["steps"] == 4 and tb["kernel_level_ms"][0] > 0
+    assert tb["kernel_level_tasks"] == ta["kernel_level_tasks"]
+    for k in ("ionized_hydrogen_fraction", "temperature", "photon_rate"):
+        assert np.array_equal(a.read(k), b.read(k))
+    with pytest.raises(Exception):
+        b.set_timing_level(7)

@@ -40,7 +40,13 @@ for i, r in enumerate(rows):
 if hi is not None:
     h = rows[hi]
     ix = {k: j for j, k in enumerate(h)}
-    body = [r for r in rows[hi + 1:] if len(r) == len(h)]
+    body = []
+    for r in rows[hi + 1:]:   # a report with several launches repeats the header block: keep the first launch
+        if len(r) != len(h) or r == h:
+            if body:
+                break
+            continue
+        body.append(r)
     tot = sum(int(r[ix["# Samples"]] or 0) for r in body) or 1
     print(f"-- per-instruction (>=1% of {tot} samples, or memory instructions) --", file=out)
     stalls = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
