@@ -110,8 +110,8 @@ def test_convergence_failure_is_not_an_error(cuda_lib):
             one(U.KILOPARSEC), one(1e120), one(1.0 * U.MEGAYEARS))
     ref = oracle.chemistry(*args, safety=0.1)
     got = gpu_chemistry(cuda_lib, *args, 1.0, 0.1, False)
-    assert ref["process"][0] == got["process"][0]
-    if ref["process"][0] == -1:
-        assert got["timescale"][0] == ref["timescale"][0] == U.MEGAYEARS / 10.0
+    assert ref["process"][0] == -1 and ref["depth"][0] == 100 and ref["attempts"][0] == 101   # the case does fail to converge
+    assert got["process"][0] == -1 and got["depth"][0] == 100 and got["attempts"][0] == 101
+    assert got["timescale"][0] == ref["timescale"][0] == U.MEGAYEARS / 10.0
     for k in ("xhii", "temperature"):
         assert_close(got[k], ref[k], RTOL, what=k)
