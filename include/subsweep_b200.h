@@ -286,7 +286,7 @@ int ssw_get_timings(ssw_handle *h, ssw_timings *out);
 int ssw_reset_timings(ssw_handle *h);
 /* 0: time only whole steps and the sweep kernel of the all-cells sweeps (four CUDA event records per step: what a
  * production host wants); 1 (default, or SSW_TIMERS): every phase of every single sweep, the breakdown the reference's
- * `Performance` timers print (src/sweep/mod.rs:262-288).  The fine level records about ten events per single sweep. */
+ * `Performance` timers print (src/sweep/mod.rs:275-283, 550, 577).  The fine level records about ten events per single sweep. */
 int ssw_set_timing_level(ssw_handle *h, int32_t level);
 
 /* -- helpers -------------------------------------------------------------------------------- */
