@@ -288,6 +288,15 @@ def pinned(n: int) -> np.ndarray:
     return torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
 
 
+def attempts_histogram(sweep) -> dict:
+    """Substep attempts of every cell's last chemistry update, in octave bins."""
+    a = sweep.chem_attempts().astype(np.int64)
+    edges = [0, 1, 2, 3, 5, 9, 17, 33, 65, 129, 257, 513, 1025, 65536]
+    counts, _ = np.histogram(a, bins=edges)
+    labels = ["0 (never updated)", "1", "2", "3-4", "5-8", "9-16", "17-32", "33-64", "65-128", "129-256", "257-512", "513-1024", ">1024"]
+    return {"bins": labels, "cells": [int(c) for c in counts], "max": int(a.max())}
+
+
 def all_cells_form(sweep) -> str:
     """Which compiled form the all-cells sweep runs in and the kernel that carries it."""
     if sweep.stat("patch_macro_tiles"):
@@ -413,6 +422,7 @@ def run_b200(args) -> None:
                               "chem_attempts": sweep.stat("chem_attempts"), "chem_cells": sweep.stat("chem_cells"),
                               "chem_max_depth": sweep.stat("chem_max_depth"), "schedule_builds": sweep.stat("schedule_builds"),
                               "all_cells_form": all_cells_form(sweep),
+                              "chem_attempts_histogram": attempts_histogram(sweep),
                               "macro_tiles": sweep.stat("patch_macro_tiles"), "patch_levels": sweep.stat("patch_levels"),
                               "patch_phases": sweep.stat("patch_phases"),
                               "mean_xhii": float(sweep.read("ionized_hydrogen_fraction").mean()),
@@ -481,7 +491,7 @@ def run_b200(args) -> None:
         t = json.loads(tfile.read_text())
         traffic, traffic_source = t["dram_bytes_per_launch"], t["source"]
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_nominal": 8000.0, "frac_nominal": achieved / 8000.0, "traffic": traffic,
         "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": traffic_source,
         "algorithmic_bytes_per_launch": b_alg * k_tasks / k_launches,
         "kernel": all_cells_form(sweep) + " of the all-cells single sweep (timestep level %d)" % lvl,
@@ -521,6 +531,7 @@ def run_b200(args) -> None:
                    "level_counts": [int(v) for v in sweep.level_counts()],
                    "chem_attempts": sweep.stat("chem_attempts"), "chem_cells": sweep.stat("chem_cells"),
                    "chem_max_depth": sweep.stat("chem_max_depth"), "wavefront_levels": sweep.stat("wavefront_levels"),
+                   "chem_attempts_histogram": attempts_histogram(sweep),
                    "schedule_builds": sweep.stat("schedule_builds"), "schedule_replays": sweep.stat("schedule_replays"),
                    "patch_macro_tiles": sweep.stat("patch_macro_tiles"), "patch_levels": sweep.stat("patch_levels"),
                    "patch_note": sweep.patch_note(),

@@ -165,6 +165,7 @@ extern "C" {
     pub fn ssw_read_begin(h: *mut ssw_handle, field: ssw_field, out: *mut f64) -> c_int;
     pub fn ssw_sync(h: *mut ssw_handle) -> c_int;
     pub fn ssw_read_levels(h: *mut ssw_handle, out: *mut u8) -> c_int;
+    pub fn ssw_read_chem_attempts(h: *mut ssw_handle, out: *mut u16) -> c_int;
     pub fn ssw_level_counts(h: *mut ssw_handle, out: *mut u64) -> c_int;
     pub fn ssw_lowest_allowed_level(h: *mut ssw_handle, out: *mut i32) -> c_int;
     pub fn ssw_time_series_compute(h: *mut ssw_handle, mass: *const f64, with_rates: i32, out: *mut ssw_time_series) -> c_int;

@@ -206,6 +206,11 @@ int ssw_read(ssw_handle *h, ssw_field field, double *out /* N, or NULL on worker
 int ssw_read_begin(ssw_handle *h, ssw_field field, double *out);
 int ssw_sync(ssw_handle *h);
 int ssw_read_levels(ssw_handle *h, uint8_t *out /* N */);
+/* Substep attempts of every cell's LAST chemistry update (perform_timestep_internal, hydrogen_only/mod.rs:394-441:
+ * 1 = the first attempt was accepted; saturates at 65535; 0 = never updated).  Diagnostic: the substep histogram of an
+ * ionization front; the library itself orders its chemistry launches by it.  Under
+ * peer-mapped sharding a rank knows the counts of the cells it owns. */
+int ssw_read_chem_attempts(ssw_handle *h, uint16_t *out /* N */);
 int ssw_level_counts(ssw_handle *h, uint64_t *out /* n_levels, cumulative: #cells with level >= l */);
 int ssw_lowest_allowed_level(ssw_handle *h, int32_t *out);
 

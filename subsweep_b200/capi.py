@@ -102,6 +102,7 @@ SYMBOLS = {
     "ssw_sync": (C.c_int, [H]),
     "ssw_time_series_compute": (C.c_int, [H, c_double_p, C.c_int32, C.POINTER(TimeSeries)]),
     "ssw_read_levels": (C.c_int, [H, C.POINTER(C.c_uint8)]),
+    "ssw_read_chem_attempts": (C.c_int, [H, C.POINTER(C.c_uint16)]),
     "ssw_level_counts": (C.c_int, [H, C.POINTER(C.c_uint64)]),
     "ssw_lowest_allowed_level": (C.c_int, [H, C.POINTER(C.c_int32)]),
     "ssw_single_sweep": (C.c_int, [H, C.c_int32]),

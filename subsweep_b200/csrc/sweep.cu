@@ -1687,6 +1687,17 @@ int ssw_read_levels(ssw_handle *h, uint8_t *out) {
     SSW_CATCH
 }
 
+int ssw_read_chem_attempts(ssw_handle *h, uint16_t *out) {
+    SSW_TRY
+    REQUIRE_HANDLE(h);
+    if (!out) ssw::fail(SSW_E_INVALID, "null output");
+    auto &s = h->s;
+    CUDA_CHECK(cudaSetDevice(s.device));
+    CUDA_CHECK(cudaMemcpyAsync(out, s.last_attempts.p, sizeof(uint16_t) * (size_t)s.N, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    SSW_CATCH
+}
+
 int ssw_level_counts(ssw_handle *h, uint64_t *out) {
     SSW_TRY
     REQUIRE_HANDLE(h);

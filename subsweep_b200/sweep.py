@@ -342,6 +342,12 @@ class Sweep:
         self._check(self.lib.ssw_read_levels(self._h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
         return out
 
+    def chem_attempts(self) -> np.ndarray:
+        """Substep attempts of every cell's last chemistry update (ssw_read_chem_attempts; 0 = never updated)."""
+        out = np.empty(self.n_cells, dtype=np.uint16)
+        self._check(self.lib.ssw_read_chem_attempts(self._h, out.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return out
+
     def level_counts(self) -> np.ndarray:
         out = np.zeros(self.parameters.num_timestep_levels, dtype=np.uint64)
         self._check(self.lib.ssw_level_counts(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))

@@ -121,3 +121,16 @@ def test_timing_level_zero_times_steps_and_all_cells_kernels_only(cuda_lib):
         assert np.array_equal(a.read(k), b.read(k))
     with pytest.raises(Exception):
         b.set_timing_level(7)
+
+
+def test_chem_attempts_read_back(cuda_lib):
+    """ssw_read_chem_attempts: the substep attempts of every cell's last chemistry update.  After one step at one timestep
+    level every cell was updated exactly once, so the per-cell counts add up to the library's attempt counter."""
+    params, g, f = make_problem("cartesian", 10, False, n_dirs=21, n_levels=1, source_rate=1e54, max_timestep_myr=1.0)
+    s = Sweep(params, g, **f)
+    assert not s.chem_attempts().any()
+    s.run_sweeps()
+    a = s.chem_attempts()
+    assert a.dtype == np.uint16 and a.shape == (g.n_cells,) and a.min() >= 1
+    assert int(a.astype(np.int64).sum()) == s.stat("chem_attempts")
+    assert a.max() > 1   # the cells next to the sources substep
