@@ -520,7 +520,7 @@ def run_b200(args) -> None:
                 "d2h_bytes_per_step": 8 * N * len(outs),
                 "rank0_wall_ms_per_step": {k: 1e3 * v / args.steps for k, v in phase.items()},
                 "note": "every rank uploads the step's Source component; rank 0 reads back the five result components "
-                        "(all ranks hold identical cell state; worker ranks only join the photon_rate all-reduce)"},
+                        "(a cell's state lives on its owner rank and is pulled at read-back; the other ranks only join the photon_rate exchange)"},
         "gpu_launches": int(total_launches),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
