@@ -174,3 +174,47 @@ def test_binary_heap_pop_order(n, nkeys):
     assert sorted(order.tolist()) == list(range(n))          # a permutation
     assert np.all(np.diff(popped.astype(np.int64)) <= 0)     # max-heap on the direction index
     assert order.tolist() == _py_heap_pop_order(keys.tolist())
+
+
+# ---------------------------------------------------------------------------------------------
+# Double entry: the rate fits typed a second time, in Python, straight from the reference's expressions
+# (src/chemistry/hydrogen_only/mod.rs:161-263), against the C restatement -- a transcription slip in either shows.
+# ---------------------------------------------------------------------------------------------
+def _fits_second_entry(t):
+    import math
+    cm3_per_s, ergs_cm3_per_s = 1e-6, 1e-7 * 1e-6
+    lam = 315614.0 / t
+    fit = math.sqrt(t) / (1.0 + math.sqrt(t / 1e5)) * math.exp(-157809.1 / t)                       # :161-164
+    c1, c2 = 1.0 / 1e5, 157809.1
+    dfit = (math.exp(-c2 / t) * (c1 * c2 * t + 0.5 * math.sqrt(c1 * t) * (2.0 * c2 + t))) / \
+           (math.sqrt(t ** 3) * math.sqrt(c1 * t) * (math.sqrt(c1 * t) + 1.0) ** 2)                 # :166-173
+    p = (lam / 2.74) ** 0.407
+    q = (315614.0 / (2.25 * t)) ** 0.376
+    return {
+        "alpha_b": 2.753e-14 * lam ** 1.5 / (1.0 + p) ** 2.242 * cm3_per_s,                          # :175-180
+        "dalpha_b": 2.753e-14 * (-math.sqrt(lam) * (p + 1.0) ** (-2.242 - 1.0) * (0.407 * 2.242 * p - 1.5 * p - 1.5))
+                    * cm3_per_s * (-315614.0 / t ** 2),                                            # :182-194
+        "recomb_cool": 3.435e-30 * t * lam ** 1.97 / (1.0 + (lam / 2.25) ** 0.376) ** 3.72 * ergs_cm3_per_s,   # :196-202
+        "drecomb_cool": 3.435e-30 * ((1.0 + q) ** (-1.0 - 3.72) * (1.0 - 1.97 + (1.0 - 1.97 + 0.376 * 3.72) * q)
+                                     * (315614.0 / t) ** 1.97) * ergs_cm3_per_s,                   # :204-216
+        "coll_ion": 5.85e-11 * fit * cm3_per_s, "dcoll_ion": 5.85e-11 * dfit * cm3_per_s,             # :218-225
+        "coll_ion_cool": 1.27e-21 * fit * ergs_cm3_per_s, "dcoll_ion_cool": 1.27e-21 * dfit * ergs_cm3_per_s,   # :227-235
+        "coll_exc_cool": 7.5e-19 / (1.0 + math.sqrt(t / 1e5)) * math.exp(-118348.0 / t) * ergs_cm3_per_s,     # :237-242
+        "brems": 1.42e-27 * math.sqrt(t) * ergs_cm3_per_s, "dbrems": 1.42e-27 / (2.0 * math.sqrt(t)) * ergs_cm3_per_s,   # :255-263
+    }
+
+
+@pytest.mark.parametrize("T", [1e1, 3e2, 1e4, 2.5e4, 1e5, 3e6, 1e7])
+def test_rate_fits_double_entry(T):
+    lib = oracle.load()
+    s = _solver(T)
+    for name, want in _fits_second_entry(T).items():
+        got = lib.orc_fit(C.byref(s), oracle.FITS[name])
+        assert got == pytest.approx(want, rel=1e-12, abs=1e-300), (name, T)
+
+
+def test_case_b_recombination_matches_the_literature_value():
+    """alpha_B(1e4 K) = 2.59e-13 cm^3/s (Hui & Gnedin 1997, the fit the reference uses via Rosdahl et al. 2013)."""
+    lib = oracle.load()
+    s = _solver(1e4)
+    assert lib.orc_fit(C.byref(s), oracle.FITS["alpha_b"]) == pytest.approx(2.59e-13 * 1e-6, rel=5e-3)
