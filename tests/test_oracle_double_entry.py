@@ -75,3 +75,191 @@ def test_python_single_sweep_equals_the_c_oracle(kind, n, n_dirs):
         np.testing.assert_allclose(mine, ref, rtol=1e-11, atol=1e-13 * scale, err_msg=name)
     ref_rate = s.read("previous_rate")
     np.testing.assert_allclose(rate, ref_rate, rtol=1e-11, atol=1e-13 * np.abs(ref_rate).max())
+
+
+# ---------------------------------------------------------------------------------------------
+# Chemistry: Solver::perform_timestep typed a second time, RECURSIVELY as the reference writes it
+# (src/chemistry/hydrogen_only/mod.rs:139-461), in numpy float64 scalars (IEEE division by zero, NaN, inf like Rust).
+# ---------------------------------------------------------------------------------------------
+F = np.float64
+INV_EPS = F(1.0) / F(np.finfo(np.float64).eps)
+KB, MP, GAMMA = F(1.380649e-23), F(1.67262192369e-27), F(5.0) / F(3.0)
+EV = F(1.602176634e-19)
+E_PHOTON, RYDBERG = F(18.028356312818811) * EV, F(13.65693) * EV
+CM3_PER_S, ERGS_CM3_PER_S, ERGS_PER_S = F(1e-6), F(1e-7) * F(1e-6), F(1e-7)
+SIG = F(2.9580524545305314e-18) * (F(0.01) * F(0.01))
+
+
+def _exp(v): return F(math.exp(v))      # glibc, like the C restatement (numpy's own SIMD exp may differ in the last bit)
+def _sqrt(v): return F(math.sqrt(v))
+def _pow(b, e): return F(math.pow(b, e))
+
+
+class PySolver:
+    def __init__(self, x, t, rho, vol, length, rate, a, prevent_cooling):
+        self.x, self.t, self.rho, self.vol, self.len, self.rate, self.a = map(F, (x, t, rho, vol, length, rate, a))
+        self.floor = (self.t, self.x) if prevent_cooling else None
+        self.attempts, self.max_depth = 0, 0
+
+    # :139-159
+    def nh(self): return self.rho / MP
+    def nh1(self): return self.nh() * self.x
+    def nh0(self): return self.nh() * (F(1.0) - self.x)
+    def ne(self): return self.nh1()
+    def mu(self): return F(1.0) / (self.x + F(1.0))
+
+    def fit(self):                                                                     # :161-164
+        t = self.t
+        return _sqrt(t) / (F(1.0) + _sqrt(t / F(1e5))) * _exp(F(-157809.1) / t)
+
+    def dfit(self):                                                                    # :166-173
+        c1, c2, t = F(1.0) / F(1e5), F(157809.1), self.t
+        return (_exp(-c2 / t) * (c1 * c2 * t + F(0.5) * _sqrt(c1 * t) * (F(2.0) * c2 + t))) / \
+               (_sqrt(t * t * t) * _sqrt(c1 * t) * ((_sqrt(c1 * t) + F(1.0)) * (_sqrt(c1 * t) + F(1.0))))
+
+    def alpha(self):                                                                   # :175-180
+        lam = F(315614.0) / self.t
+        return F(2.753e-14) * _pow(lam, F(1.5)) / _pow(F(1.0) + _pow(lam / F(2.74), F(0.407)), F(2.242)) * CM3_PER_S
+
+    def dalpha(self):                                                                  # :182-194
+        lam = F(315614.0) / self.t
+        dlam = F(-315614.0) / (self.t * self.t)
+        c1, c2, c3 = F(1.0) / F(2.74), F(0.407), F(2.242)
+        p = _pow(c1 * lam, c2)
+        d = -_sqrt(lam) * _pow(p + F(1.0), -c3 - F(1.0)) * (c2 * c3 * p - F(1.5) * p - F(1.5))
+        return (F(2.753e-14) * d) * CM3_PER_S * dlam
+
+    def rec_cool(self):                                                                # :196-202
+        lam = F(315614.0) / self.t
+        return (F(3.435e-30) * self.t * _pow(lam, F(1.97)) / _pow(F(1.0) + _pow(lam / F(2.25), F(0.376)), F(3.72))) * ERGS_CM3_PER_S
+
+    def drec_cool(self):                                                               # :204-216
+        c1, c2, c3, c4, c5, t = F(315614.0), F(1.97), F(0.376), F(3.72), F(2.25), self.t
+        p = _pow(c1 / (c5 * t), c3)
+        der = _pow(F(1.0) + p, F(-1.0) - c4) * (F(1.0) - F(1.0) * c2 + (F(1.0) - F(1.0) * c2 + c3 * c4) * p) * _pow(c1 / t, c2)
+        return (F(3.435e-30) * der) * ERGS_CM3_PER_S
+
+    def beta(self): return (F(5.85e-11) * self.fit()) * CM3_PER_S                      # :218-225
+    def dbeta(self): return (F(5.85e-11) * self.dfit()) * CM3_PER_S
+    def ion_cool(self): return (F(1.27e-21) * self.fit()) * ERGS_CM3_PER_S             # :227-235
+    def dion_cool(self): return (F(1.27e-21) * self.dfit()) * ERGS_CM3_PER_S
+
+    def exc_cool(self):                                                                # :237-242
+        t = self.t
+        return (F(7.5e-19) / (F(1.0) + _sqrt(t / F(1e5))) * _exp(F(-118348.0) / t)) * ERGS_CM3_PER_S
+
+    def dexc_cool(self):                                                               # :244-253
+        t, c1, c2, c3 = self.t, F(7.5e-19), F(118348.0), F(1.0) / F(1e5)
+        s = _sqrt(c3 * t)
+        return ((c1 * _exp(-c2 / t) * (c2 * c3 * t - F(0.5) * c3 * (t * t) + c2 * s)) /
+                ((t * t) * s * ((F(1.0) + s) * (F(1.0) + s)))) * ERGS_CM3_PER_S
+
+    def brems(self): return (F(1.42e-27) * _sqrt(self.t)) * ERGS_CM3_PER_S           # :255-263
+    def dbrems(self): return (F(1.42e-27) / (F(2.0) * _sqrt(self.t))) * ERGS_CM3_PER_S
+
+    def _x4(self):
+        x = F(2.727) / self.a
+        return (x * x) * (x * x)
+
+    def compton(self): return (F(1.017e-37) * self._x4() * (self.t - F(2.727) / self.a)) * ERGS_PER_S   # :265-273
+    def dcompton(self): return (F(1.017e-37) * self._x4()) * ERGS_PER_S
+
+    def cooling(self):                                                                 # :275-287
+        ne, n0, n1 = self.ne(), self.nh0(), self.nh1()
+        return (self.exc_cool() + self.ion_cool()) * ne * n0 + self.rec_cool() * ne * n1 + self.brems() * ne * n1 + self.compton() * ne
+
+    def dcooling(self):                                                                # :289-302
+        ne, n0, n1 = self.ne(), self.nh0(), self.nh1()
+        return (self.dexc_cool() + self.dion_cool()) * ne * n0 + self.drec_cool() * ne * n1 + self.dbrems() * ne * n1 + self.dcompton() * ne
+
+    def newly_ionized(self, h):                                                        # :312-319
+        return (h * self.rate) * (F(1.0) - _exp(-self.nh0() * SIG * self.len))
+
+    def heating(self, h):                                                              # :321-325
+        return self.newly_ionized(h) / self.vol * (E_PHOTON - RYDBERG) / h
+
+    def photoionization(self, h):                                                      # :327-332
+        return self.newly_ionized(h) / (self.nh0() * self.vol) / h
+
+    def dtemperature(self, h):                                                         # :304-310
+        k = (GAMMA - F(1.0)) * MP / (self.rho * KB)
+        lam = self.heating(h) - self.cooling()
+        dlam = -self.dcooling()
+        mu = self.mu()
+        return k * mu * lam * h / (F(1.0) - k * mu * dlam * h)
+
+    def dxhii(self, h):                                                                # :334-354
+        nh, ne = self.nh(), self.ne()
+        alpha, dalpha, beta, dbeta = self.alpha(), self.dalpha(), self.beta(), self.dbeta()
+        c = beta * ne + self.photoionization(h)
+        mu = self.mu()
+        d = alpha * ne
+        dcdx = nh * beta - ne * self.t * mu * F(1.0) * dbeta
+        dddx = nh * alpha - ne * self.t * mu * F(1.0) * dalpha
+        j = dcdx - (c + d) - self.x * (dcdx + dddx)
+        return h * (c - self.x * (c + d)) / (F(1.0) - j * h)
+
+    def clamp(self):                                                                   # :356-369
+        lo = self.floor[1] if self.floor else F(1e-10)
+        self.x = min(max(self.x, lo), F(1.0) - F(1e-10))
+        if self.floor and self.t < self.floor[0]:
+            self.t = self.floor[0]
+
+    @staticmethod
+    def update(value, change, max_allowed, h):                                         # :444-461 (f64::min ignores a NaN)
+        rel = abs(change / value)
+        rel = INV_EPS if rel != rel else min(rel, INV_EPS)
+        if rel > max_allowed:
+            return None
+        return value + change, h * (max_allowed / rel)
+
+    def try_update(self, h, safety):                                                   # :371-392
+        r = self.update(self.t, self.dtemperature(h), safety, h)
+        if r is None:
+            return None
+        self.t, t_rec = r
+        r = self.update(self.x, self.dxhii(h), safety, h)
+        if r is None:
+            return None
+        self.x, x_rec = r
+        self.clamp()
+        return t_rec if t_rec < x_rec else x_rec
+
+    def internal(self, h, safety, depth):                                              # :394-424
+        self.clamp()
+        saved = (self.t, self.x)
+        if depth > 100:
+            raise OverflowError("TimestepConvergenceFailed")
+        self.attempts += 1
+        self.max_depth = max(self.max_depth, depth)
+        r = self.try_update(h, safety)
+        if r is None:
+            self.t, self.x = saved
+            self.internal(h / F(2.0), safety, depth + 1)
+            return self.internal(h / F(2.0), safety, depth + 1)
+        return r
+
+    def perform(self, h, safety):                                                      # :426-441
+        try:
+            return self.internal(F(h), F(safety), 0), False
+        except OverflowError:
+            return F(h) / F(10.0), True
+
+
+def test_python_recursive_chemistry_equals_the_c_oracle():
+    z = np.load(__import__("pathlib").Path(__file__).parent / "golden" / "chemistry_cells.npz")
+    cols = [z[k] for k in ("xhii", "temperature", "density", "volume", "length", "rate", "timestep")]
+    # every eighth cell plus the heaviest substeppers of the set
+    heavy = np.argsort(z["pc1_attempts"])[-12:]
+    pick = np.unique(np.concatenate([np.arange(0, len(cols[0]), 8), heavy]))
+    assert z["pc1_attempts"][pick].max() > 50
+    with np.errstate(all="ignore"):
+        for pc in (False, True):
+            ref = oracle.chemistry(*(c[pick] for c in cols), scale_factor=0.5, safety=0.1, prevent_cooling=pc)
+            for j, i in enumerate(pick):
+                s = PySolver(*(c[i] for c in cols[:6]), 0.5, pc)
+                timescale, failed = s.perform(cols[6][i], 0.1)
+                assert s.attempts == ref["attempts"][j] and s.max_depth == ref["depth"][j], (i, pc)
+                assert failed == (ref["process"][j] == -1)
+                for got, want in ((s.x, ref["xhii"][j]), (s.t, ref["temperature"][j]), (timescale, ref["timescale"][j])):
+                    assert got == pytest.approx(want, rel=1e-12, abs=0.0), (i, pc)
