@@ -263,3 +263,189 @@ def test_python_recursive_chemistry_equals_the_c_oracle():
                 assert failed == (ref["process"][j] == -1)
                 for got, want in ((s.x, ref["xhii"][j]), (s.t, ref["temperature"][j]), (timescale, ref["timescale"][j])):
                     assert got == pytest.approx(want, rel=1e-12, abs=0.0), (i, pc)
+
+
+# ---------------------------------------------------------------------------------------------
+# The whole of Sweep::run_sweeps, a second time: timestep levels, partial active sets, periodic faces read in the
+# order Rust's BinaryHeap pops the tasks (src/sweep/mod.rs:258-589, task.rs:25-35, active_list.rs, timestep_state.rs).
+# ---------------------------------------------------------------------------------------------
+class PyBinaryHeap:
+    """std::collections::BinaryHeap of (key, payload) compared by key only (SURVEY.md appendix B)."""
+
+    def __init__(self, items):
+        self.data = list(items)
+        n = len(self.data) // 2
+        while n > 0:
+            n -= 1
+            self._sift_down_range(n, len(self.data))
+
+    def _sift_down_range(self, pos, end):
+        d = self.data
+        elem = d[pos]
+        child = 2 * pos + 1
+        while end >= 2 and child <= end - 2:
+            if d[child][0] <= d[child + 1][0]:
+                child += 1
+            if elem[0] >= d[child][0]:
+                d[pos] = elem
+                return
+            d[pos] = d[child]
+            pos = child
+            child = 2 * pos + 1
+        if child == end - 1 and elem[0] < d[child][0]:
+            d[pos] = d[child]
+            pos = child
+        d[pos] = elem
+
+    def _sift_up(self, start, pos):
+        d = self.data
+        elem = d[pos]
+        while pos > start:
+            parent = (pos - 1) // 2
+            if elem[0] <= d[parent][0]:
+                break
+            d[pos] = d[parent]
+            pos = parent
+        d[pos] = elem
+
+    def push(self, item):
+        self.data.append(item)
+        self._sift_up(0, len(self.data) - 1)
+
+    def pop(self):
+        d = self.data
+        if not d:
+            return None
+        item = d.pop()
+        if d:
+            item, d[0] = d[0], item
+            end, pos, elem, child = len(d), 0, d[0], 1     # sift_down_to_bottom(0)
+            while end >= 2 and child <= end - 2:
+                if d[child][0] <= d[child + 1][0]:
+                    child += 1
+                d[pos] = d[child]
+                pos = child
+                child = 2 * pos + 1
+            if child == end - 1:
+                d[pos] = d[child]
+                pos = child
+            d[pos] = elem
+            self._sift_up(0, pos)
+        return item
+
+
+class PySweep:
+    def __init__(self, params, g, density, ionized_hydrogen_fraction, temperature, source, scale_factor=1.0):
+        self.g, self.p, self.a = g, params, scale_factor
+        self.dirs = Directions.from_spec(params.directions).xyz
+        self.N, self.D, self.L = g.n_cells, len(self.dirs), params.num_timestep_levels
+        self.off = g.face_offsets.astype(np.int64)
+        self.rho, self.src = density.astype(np.float64), source.astype(np.float64)
+        self.x, self.T = ionized_hydrogen_fraction.astype(np.float64).copy(), temperature.astype(np.float64).copy()
+        self.inc, self.out, self.per = (np.zeros((self.N, self.D)) for _ in range(3))
+        self.prev, self.tau, self.ts = np.zeros(self.N), np.zeros(self.N), np.zeros(self.N)
+        self.level = np.full(self.N, self.L - 1, dtype=np.int64)
+        self.lowest, self.first_done = self.L - 1, False
+        self.dot = np.empty((self.D, g.n_faces))
+        for d, (dx, dy, dz) in enumerate(self.dirs):       # glam DVec3::dot: x*x + y*y + z*z, left to right
+            self.dot[d] = (g.face_normal[:, 0] * dx + g.face_normal[:, 1] * dy) + g.face_normal[:, 2] * dz
+
+    def active_in_bin_order(self, cur):                    # active_list.rs:55-66, 143-153
+        return [c for lvl in range(cur, self.L) for c in range(self.N) if self.level[c] == lvl]
+
+    def single_sweep(self, cur):                           # mod.rs:274-289
+        g, off, D = self.g, self.off, self.D
+        act = self.active_in_bin_order(cur)
+        is_active = self.level >= cur
+        miss = {}
+        for c in act:                                      # init_counts :346-386
+            for d in range(D):
+                miss[c, d] = sum(1 for f in range(off[c], off[c + 1])
+                                 if self.dot[d, f] < 0.0 and g.face_kind[f] == 0 and is_active[g.face_neighbour[f]])
+        heap = PyBinaryHeap([(d, c) for d in range(D) for c in act if miss[c, d] == 0])   # get_initial_tasks :388-398
+        thr = self.p.significant_rate_threshold
+        while True:                                        # solve :291-314
+            task = heap.pop()
+            if task is None:
+                break
+            d, c = task
+            self.inc[c, d] = max(self.inc[c, d], 0.0)      # make_positive :418
+            total = (self.inc[c, d] + self.src[c] / D) + self.per[c, d]
+            nhi = self.rho[c] / U.PROTON_MASS * (1.0 - self.x[c])
+            o = 0.0 if total < thr else total * math.exp(-nhi * SIGMA * g.cell_size[c])
+            delta = o - self.out[c, d]
+            self.out[c, d] = o
+            down = [f for f in range(off[c], off[c + 1]) if self.dot[d, f] > 0.0]
+            ttot = 0.0
+            for f in down:
+                ttot += g.face_area[f] * self.dot[d, f]
+            for f in down:
+                share = delta * ((g.face_area[f] * self.dot[d, f]) / ttot)
+                nb, kind = g.face_neighbour[f], g.face_kind[f]
+                if kind == 0:                              # handle_local_neighbour :487-503
+                    self.inc[nb, d] += share
+                    if is_active[nb]:
+                        miss[nb, d] -= 1
+                        if miss[nb, d] == 0:
+                            heap.push((d, nb))
+                elif kind == 2:                            # handle_local_periodic_neighbour :505-513
+                    self.per[nb, d] += share
+        assert all(v == 0 for v in miss.values())
+        for c in act:                                      # update_chemistry :549-574
+            dt = self.p.max_timestep * 0.5 ** int(self.level[c])
+            rate = 0.0
+            for d in range(D):
+                rate = rate + ((self.inc[c, d] + self.src[c] / D) + self.per[c, d])
+            with np.errstate(all="ignore"):
+                if abs(rate) < abs(thr):
+                    rel = F(0.0)
+                else:
+                    rel = abs(F(abs(rate - self.prev[c])) / F(rate))
+                    rel = INV_EPS if rel != rel else min(rel, INV_EPS)
+                self.prev[c] = rate
+                t_rate = F(dt) / rel
+                s = PySolver(self.x[c], self.T[c], self.rho[c], g.cell_volume[c], g.cell_size[c], rate, self.a,
+                             self.p.prevent_cooling)
+                t_chem, _ = s.perform(dt, self.p.chemistry_timestep_safety_factor)
+            self.x[c], self.T[c], self.ts[c] = s.x, s.t, t_chem
+            self.tau[c] = t_rate if t_rate < t_chem else t_chem                       # Timescale::min, timescale.rs:32-38
+
+    def run_sweeps(self):                                  # mod.rs:258-272, timestep_state.rs
+        counts = [int((self.level >= l).sum()) for l in range(self.L)]
+        num = self.L - self.lowest
+        for i in range(2 ** (num - 1)):
+            first_bit = (i & -i).bit_length() - 1 if i else num - 1
+            cur = self.lowest + (num - 1 - first_bit)
+            if counts[cur] > 0:
+                self.single_sweep(cur)
+        elapsed = self.p.max_timestep * 0.5 ** self.lowest
+        if self.first_done and self.lowest > 0:
+            self.lowest -= 1
+        self.first_done = True
+        with np.errstate(all="ignore"):
+            for c in range(self.N):                        # update_timestep_levels :576-589, timestep_level.rs:27-36
+                ratio = F(self.p.max_timestep) / (F(self.p.timestep_safety_factor) * F(self.tau[c]))
+                lv = np.ceil(np.log2(ratio))
+                lv = 0 if (lv != lv or lv < 0) else (2 ** 62 if lv == np.inf else int(lv))   # Rust `as usize` saturates
+                self.level[c] = max(min(lv, self.L - 1), self.lowest)
+        return elapsed
+
+
+@pytest.mark.parametrize("kind,n,periodic,n_dirs,n_levels", [("voronoi", 3, True, 16, 2), ("cartesian", 4, True, 21, 3),
+                                                             ("jittered", 4, False, 16, 3)])
+def test_python_run_sweeps_equals_the_c_oracle(kind, n, periodic, n_dirs, n_levels):
+    params, g, f = make_problem(kind, n, periodic, n_dirs=n_dirs, n_levels=n_levels, source_rate=3e51, max_timestep_myr=0.5)
+    mine = PySweep(params, g, **f)
+    ref = oracle.OracleSweep(params, g, **f, periodic_mode=oracle.PERIODIC_HEAP)
+    for step in range(n_levels + 2):
+        assert mine.run_sweeps() == ref.run_sweeps()
+        assert np.array_equal(mine.level, ref.levels()), step
+        for name, arr in (("ionized_hydrogen_fraction", mine.x), ("temperature", mine.T), ("timestep", mine.ts),
+                          ("change_timescale", mine.tau), ("previous_rate", mine.prev)):
+            want = ref.read(name)
+            np.testing.assert_allclose(arr, want, rtol=1e-10, atol=1e-12 * np.abs(want[np.isfinite(want)]).max(), err_msg=f"{name} step {step}")
+        for name, arr in (("outgoing", mine.out), ("incoming", mine.inc), ("periodic", mine.per)):
+            want = ref.dir_state(name)
+            np.testing.assert_allclose(arr, want, rtol=1e-10, atol=1e-12 * max(np.abs(want).max(), 1e-300), err_msg=f"{name} step {step}")
+    if periodic and kind != "cartesian":
+        assert ref.stat("nonlagged_periodic_reads") > 0   # the heap order did matter on this grid
