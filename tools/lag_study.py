@@ -5,7 +5,7 @@ order-independent definition the CUDA path implements.
 
     python tools/lag_study.py [--n 32] [--myr 1 2 4] [--source 1e52 1e54]
 
-Workload: bench.py's Voronoi variant of the headline box at n^3 cells (log-normal density, point sources at the density
+Workload: bench.py's headline box (--grid cartesian) or its Voronoi variant (default) at n^3 cells (log-normal density, point sources at the density
 peaks, 84 directions, 4 timestep levels).  Writes one JSON line per (source strength, time) to stdout."""
 import argparse
 import json
@@ -24,12 +24,13 @@ import oracle  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=32)
+    ap.add_argument("--grid", choices=("voronoi", "cartesian"), default="voronoi")
     ap.add_argument("--dirs", type=int, default=84)
     ap.add_argument("--levels", type=int, default=4)
     ap.add_argument("--myr", type=float, nargs="+", default=[1.0, 2.0, 4.0])
     ap.add_argument("--source", type=float, nargs="+", default=[1e52, 1e54])
     args = ap.parse_args()
-    params, g, f = bench.build_workload(args.n, "voronoi", args.dirs, args.levels)
+    params, g, f = bench.build_workload(args.n, args.grid, args.dirs, args.levels)
     for strength in args.source:
         fields = dict(f)
         fields["source"] = np.where(f["source"] > 0, strength, 0.0)
@@ -46,7 +47,7 @@ def main():
             rel = np.abs(xa - xb) / np.maximum(xb, 1e-300)
             big = xb > 1e-3                      # cells that are noticeably ionized
             print(json.dumps({
-                "cells": int(g.n_cells), "directions": args.dirs, "levels": args.levels, "source_per_s": strength,
+                "grid": args.grid, "cells": int(g.n_cells), "directions": args.dirs, "levels": args.levels, "source_per_s": strength,
                 "time_myr": t_sim / 3.15576e13, "tasks": int(a.stat("tasks_solved")),
                 "nonlagged_periodic_reads": int(a.stat("nonlagged_periodic_reads")),
                 "levels_equal": bool(np.array_equal(a.levels(), b.levels())),
