@@ -7,7 +7,9 @@ src/sweep/mod.rs:258-289, 549-589), run on all host threads as direction shards 
 task-queue algorithm per direction; directions never interact inside a sweep).
 
 * config 2-C  128^3 Cartesian periodic box, log-normal density, 64 sources, 84 directions, 4 levels, to 1 Myr
-              (periodic Cartesian: heap order == lagged, tests/test_golden.py) -- every cell compared;
+              (compared with the oracle's lagged periodic reads; on this workload the reference's heap order reads the
+              same values -- zero non-lagged reads, profiles/lag_study_cartesian32.jsonl) -- every
+              cell compared;
 * config 4    chemistry-stiff ionization front (dense neutral slab, 5e54 /s source, 21 directions, 4 levels) at 48^3:
               deep substepping on both sides, levels bit-exact at every step, substep-path flips counted;
 * config 1    benches/sweep: the FULL 32^3 random-point Voronoi grid, non-periodic, 84 directions, 1 and 3 levels,
